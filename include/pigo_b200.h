@@ -1,0 +1,160 @@
+/*
+ * pigo_b200.h -- C-ABI of libpigo_b200.so, the B200 (sm_100a) drop-in for the
+ * detection path of esimov/pigo (package "pigo", import github.com/esimov/pigo/core).
+ *
+ * Every entry point states the reference interface it replaces (file:line under the
+ * reference tree).  The Go shim that binds these through cgo is go/pigo/ (see
+ * INTEGRATION.md); the C++ mirror is include/pigo_b200.hpp; the Python/ctypes mirror used
+ * by the tests and bench.py is pigo_b200/__init__.py.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no CUDA/torch types (streams travel as void*).
+ *  - every function returns a pigo_status (0 = ok, <0 = error); pigo_last_error() returns
+ *    a thread-local message for the last failure on the calling thread.
+ *  - the library NEVER falls back to a CPU path: without a usable sm_100 device every
+ *    compute entry point fails with PIGO_E_NODEVICE / PIGO_E_CUDA.
+ *  - the caller owns all input/output buffers.  Host buffers are copied inside the call
+ *    (cgo rule: C keeps no Go pointer after return).  Handles own their device tables and
+ *    are immutable after creation; compute calls on one handle may run concurrently from
+ *    several OS threads (scratch comes from an internal per-handle pool).
+ *  - output capacity is supplied by the caller.  If more results exist than fit, the call
+ *    stores the first `cap` (in reference order), sets *n_out / n_out[i] to the REQUIRED
+ *    count and returns PIGO_E_CAP; the caller retries with a larger buffer.
+ */
+#ifndef PIGO_B200_H_
+#define PIGO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define PIGO_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  PIGO_OK = 0,
+  PIGO_E_INVALID = -1,  /* bad argument / malformed cascade (the reference panics, core/pigo.go:64,81) */
+  PIGO_E_CUDA = -2,     /* CUDA runtime failure; see pigo_last_error() */
+  PIGO_E_CAP = -3,      /* output capacity too small; n_out holds the required count */
+  PIGO_E_NOMEM = -4,
+  PIGO_E_NODEVICE = -5  /* no sm_100 device visible: there is no CPU fallback */
+} pigo_status;
+
+/* Where the caller's frame / output buffers live. */
+#define PIGO_MEM_HOST 0u          /* pageable or pinned host memory; copies happen inside the call */
+#define PIGO_FRAMES_DEVICE 1u     /* `frames` is a device pointer on the active device            */
+#define PIGO_OUT_DEVICE 2u        /* `out` and `n_out` are device pointers; the call is fully      */
+                                  /* asynchronous on `stream` and returns without synchronising;   */
+                                  /* PIGO_E_CAP is then NOT reported (check n_out[i] > cap later)  */
+
+/* pigo.Detection (core/pigo.go:195-200): Row, Col, Scale int; Q float32.  16 bytes. */
+typedef struct {
+  int32_t row, col, scale;
+  float q;
+} pigo_det;
+
+/* pigo.Puploc (core/puploc.go:14-19): Row, Col int; Scale float32; Perturbs int. */
+typedef struct {
+  int32_t row, col;
+  float scale;
+  int32_t perturbs;
+} pigo_point;
+
+typedef struct pigo_cascade pigo_cascade; /* pigo.Pigo          (core/pigo.go:37-43)   */
+typedef struct pigo_puploc pigo_puploc;   /* pigo.PuplocCascade (core/puploc.go:23-30) */
+
+/* ---- library -------------------------------------------------------------------------- */
+const char *pigo_last_error(void);
+int pigo_version(void);
+/* Binds the calling thread (and, by default, the process) to CUDA device `device`;
+ * verifies it is compute capability 10.x.  Called implicitly with device 0 if omitted. */
+int pigo_init(int device);
+int pigo_shutdown(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t pigo_launch_count(void);
+/* Pinned host memory for zero-staging H2D copies of frame batches. */
+int pigo_alloc_pinned(void **ptr, size_t bytes);
+int pigo_free_pinned(void *ptr);
+
+/* ---- face cascade: (*Pigo).Unpack, core/pigo.go:51-110 --------------------------------- */
+/* Parses the `facefinder` binary layout (8 ignored bytes, u32 depth, u32 ntrees, then per
+ * tree 4*2^d-4 int8 codes, 2^d f32 leaves, 1 f32 threshold) and uploads the device tables.
+ * Returns PIGO_E_INVALID where the reference would panic on a short packet. */
+int pigo_cascade_create(const uint8_t *packet, size_t len, pigo_cascade **out);
+void pigo_cascade_destroy(pigo_cascade *c);
+int pigo_cascade_info(const pigo_cascade *c, uint32_t *tree_depth, uint32_t *tree_num);
+
+/* Scale ladder / grid arithmetic of RunCascade (core/pigo.go:226-231,:255), computed on the
+ * host in float64 exactly as the reference does.  `scales` may be NULL. */
+int pigo_scale_ladder(int min_size, int max_size, double scale_factor, int *scales, int cap, int *n_out);
+int64_t pigo_count_windows(int rows, int cols, int min_size, int max_size, double shift_factor, double scale_factor);
+
+/* ---- (*Pigo).RunCascade(cp CascadeParams, angle float64) []Detection, core/pigo.go:212-258
+ * CascadeParams{ImageParams{Pixels,Rows,Cols,Dim},MinSize,MaxSize,ShiftFactor,ScaleFactor}
+ * (core/pigo.go:16-34) is passed flattened.  Output order = the reference's emission order
+ * (scale-major, then row, then col); Q is bit-identical to classifyRegion /
+ * classifyRotatedRegion (core/pigo.go:113-191).  angle > 1 is clamped to 1 (:233-235). */
+int pigo_run_cascade(const pigo_cascade *c, const uint8_t *pixels, int rows, int cols, int dim,
+                     int min_size, int max_size, double shift_factor, double scale_factor, double angle,
+                     pigo_det *out, int cap, int *n_out);
+
+/* Additive batch form: `nframes` frames of identical geometry, `frame_stride` bytes apart.
+ * out is [nframes][cap_per_frame], n_out is [nframes].  `flags` is a PIGO_* memory mask;
+ * `stream` is a cudaStream_t (NULL = the library's own stream). */
+int pigo_run_cascade_batch(const pigo_cascade *c, const uint8_t *frames, int nframes, size_t frame_stride,
+                           int rows, int cols, int dim, int min_size, int max_size, double shift_factor,
+                           double scale_factor, double angle, pigo_det *out, int cap_per_frame, int *n_out,
+                           unsigned flags, void *stream);
+
+/* ---- (*Pigo).ClusterDetections(detections []Detection, iouThreshold float64) []Detection,
+ * core/pigo.go:262-308.  Like the reference it SORTS `dets` in place by Q ascending (ties keep
+ * their input order: a stable sort; Go's sort.Slice leaves tie order unspecified).  */
+int pigo_cluster(pigo_det *dets, int n, double iou_threshold, pigo_det *out, int cap, int *n_out);
+/* Batch form over the output layout of pigo_run_cascade_batch: dets is [nframes][cap_per_frame]
+ * with n[i] valid entries (n[i] > cap_per_frame is treated as cap_per_frame). */
+int pigo_cluster_batch(pigo_det *dets, const int *n, int nframes, int cap_per_frame, double iou_threshold,
+                       pigo_det *out, int out_cap_per_frame, int *n_out, unsigned flags, void *stream);
+
+/* ---- pupil / landmark cascades: (*PuplocCascade).UnpackCascade, core/puploc.go:38-103 --- */
+int pigo_puploc_create(const uint8_t *packet, size_t len, pigo_puploc **out);
+void pigo_puploc_destroy(pigo_puploc *p);
+int pigo_puploc_info(const pigo_puploc *p, uint32_t *stages, float *scale_mul, uint32_t *trees, uint32_t *depth);
+
+/* ---- (*PuplocCascade).RunDetector(pl Puploc, img ImageParams, angle float64, flipV bool) *Puploc,
+ * core/puploc.go:239-277, for `nseeds` independent seeds on one image.
+ * seeds[i].perturbs must be 0..63 (the reference panics above 63).  The reference draws
+ * 3*perturbs values from the global math/rand stream (core/puploc.go:248-250), which is
+ * auto-seeded and therefore not reproducible; here the caller either injects them
+ * (`randoms` = [nseeds][63][3] float32 in [0,1), row/col/scale order) or passes NULL and the
+ * library draws them from a counter-based generator keyed by (`rng_seed`, seed index).
+ * Slots >= perturbs of the 63-entry pool are zero (fresh sync.Pool object, :228-236).
+ * flipv: per-seed array (0/1) or NULL for all-false.  out[i].perturbs is 0 like the reference's. */
+int pigo_puploc_run(const pigo_puploc *p, const pigo_point *seeds, int nseeds, const float *randoms,
+                    uint64_t rng_seed, const uint8_t *pixels, int rows, int cols, int dim, double angle,
+                    const uint8_t *flipv, pigo_point *out, unsigned flags, void *stream);
+
+/* ---- (*PuplocCascade).GetLandmarkPoint(leftEye, rightEye *Puploc, img, perturb, flipV) *Puploc,
+ * core/flploc.go:36-57: seed arithmetic in float64 on the host, then RunDetector(angle 0). */
+int pigo_get_landmark_point(const pigo_puploc *p, const pigo_point *left_eye, const pigo_point *right_eye,
+                            const uint8_t *pixels, int rows, int cols, int dim, int perturb, int flipv,
+                            const float *randoms, uint64_t rng_seed, pigo_point *out);
+
+/* ---- tuning / introspection (not part of the reference surface) ------------------------- */
+/* Selects the scan implementation: 0 = auto (default), 1 = gather kernel only (every window
+ * through global-memory gathers), 2 = tiled (shared-memory pixel tiles) + gather for the rest. */
+int pigo_set_option(const char *name, int64_t value);
+int64_t pigo_get_option(const char *name);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIGO_B200_H_ */

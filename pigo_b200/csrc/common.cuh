@@ -1,0 +1,96 @@
+// common.cuh -- shared device/host structures of libpigo_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pigo_b200.h"
+
+namespace pigo {
+
+// One entry of the scale ladder of RunCascade (core/pigo.go:226-231,:255), computed on the host
+// in float64 exactly like the reference; the kernels only consume the resulting integers.
+struct ScaleEntry {
+  int32_t s;        // window size "scale"
+  int32_t step;     // int(max(ShiftFactor*scale, 1))
+  int32_t off;      // scale/2 + 1
+  int32_t nrows;    // grid rows  : floor((Rows-2*off)/step)+1 (0 if empty)
+  int32_t ncols;    // grid cols
+  uint32_t wbase;   // index of this scale's first window in the frame's emission order
+  uint32_t nwin;    // nrows*ncols
+  uint32_t pad;
+};
+
+// Face cascade tables on the device.  `codes` keeps the reference's in-memory layout
+// (core/pigo.go:79-86): 4 zero bytes, then 4*2^d-4 int8 codes per tree, so node idx (1-based heap)
+// sits at byte 4*idx of its tree.  Everything is read-only after pigo_cascade_create.
+struct FaceTables {
+  const int8_t* codes;   // [ntrees][4*leaves]
+  const float* preds;    // [ntrees][leaves]
+  const float* thresh;   // [ntrees]
+  int32_t depth, ntrees, leaves;
+};
+
+// Unsorted detection as produced by the scan kernels: the in-frame window index doubles as the
+// sort key that restores the reference's emission order (scale, row, col).
+struct RawDet {
+  uint32_t wid;
+  float q;
+};
+
+// A window whose evaluation continues in the deep kernel from tree `tree` with partial score `acc`.
+struct DeepItem {
+  uint32_t wid;
+  int32_t frame;
+  int32_t tree;
+  float acc;
+};
+
+struct ScanArgs {
+  FaceTables tab;
+  const uint8_t* frames;
+  size_t frame_stride;
+  int32_t nframes, rows, cols, dim;
+  const ScaleEntry* plan;
+  int32_t nscales;
+  uint32_t wins_per_frame;
+  // rotated path (angle > 0): table slot int(32*a), core/pigo.go:159-160
+  int32_t rot_slot;  // -1 = unrotated
+  // outputs
+  RawDet* raw;          // [nframes][cap]
+  int32_t* raw_count;   // [nframes]
+  int32_t cap;
+  // work distribution
+  unsigned long long* chunk_counter;
+  uint32_t chunk;             // windows per chunk
+  uint32_t chunks_per_frame;
+  // gather-kernel window filter: only scales with index in [scale_lo, scale_hi) (tiled kernel takes the rest)
+  int32_t scale_lo, scale_hi;
+  // deep queue (optional)
+  DeepItem* deep;
+  unsigned int* deep_count;
+  uint32_t deep_cap;
+  int32_t deep_tree;  // hand over to the deep kernel when an item reaches this tree (>= ntrees: never)
+};
+
+__device__ __constant__ int c_qcos[33] = {256, 251, 236, 212, 181, 142, 97, 49, 0, -49, -97, -142, -181, -212, -236, -251, -256,
+                                          -251, -236, -212, -181, -142, -97, -49, 0, 49, 97, 142, 181, 212, 236, 251, 256};
+__device__ __constant__ int c_qsin[33] = {0, 49, 97, 142, 181, 212, 236, 251, 256, 251, 236, 212, 181, 142, 97, 49, 0,
+                                          -49, -97, -142, -181, -212, -236, -251, -256, -251, -236, -212, -181, -142, -97, -49, 0};
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// Finds the ladder entry that contains in-frame window index `wid` (binary search over wbase).
+__device__ __forceinline__ int find_scale(const ScaleEntry* __restrict__ plan, int nscales, uint32_t wid) {
+  int lo = 0, hi = nscales - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&plan[mid].wbase) <= wid) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+}  // namespace pigo

@@ -1,0 +1,136 @@
+// host.h -- host-side declarations shared by the translation units of libpigo_b200.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pigo {
+
+int set_err(int code, const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+struct Options {
+  std::atomic<long long> scan_mode{0};      // 0 auto, 1 gather only, 2 tiled + gather
+  std::atomic<long long> chunk{256};        // windows per work chunk of the gather kernel
+  std::atomic<long long> deep_tree{0};      // 0 = auto
+  std::atomic<long long> gather_ctas_per_sm{0};
+  std::atomic<long long> tile_max_scale{0}; // 0 = auto
+  bool set(const std::string& k, long long v) {
+    if (k == "scan_mode") scan_mode = v; else if (k == "chunk") chunk = v; else if (k == "deep_tree") deep_tree = v;
+    else if (k == "gather_ctas_per_sm") gather_ctas_per_sm = v; else if (k == "tile_max_scale") tile_max_scale = v;
+    else return false;
+    return true;
+  }
+  long long get(const std::string& k) const {
+    if (k == "scan_mode") return scan_mode; if (k == "chunk") return chunk; if (k == "deep_tree") return deep_tree;
+    if (k == "gather_ctas_per_sm") return gather_ctas_per_sm; if (k == "tile_max_scale") return tile_max_scale;
+    return -1;
+  }
+};
+extern Options g_opt;
+
+struct PuplocTables {
+  const int8_t* codes;  // [stages*trees][4*leaves-4]
+  const float* preds;   // [stages*trees][leaves][2]
+  int32_t stages, trees, depth, leaves;
+  float scales;
+};
+
+
+// ---- workspace -----------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return PIGO_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+      cudaGetLastError();
+      return set_err(PIGO_E_NOMEM, "cudaMalloc(%zu) failed", want);
+    }
+    cap = want;
+    return PIGO_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Workspace {
+  cudaStream_t stream = nullptr;
+  DevBuf frames, raw, counters, out, nout, plan, deep, tiles, scratch_a, scratch_b, scratch_c;
+  // cached plan
+  std::vector<ScaleEntry> plan_host;
+  uint64_t wins = 0;
+  int p_rows = -1, p_cols = -1, p_min = 0, p_max = 0;
+  double p_shift = 0, p_scale = 0;
+  void* pinned = nullptr;
+  size_t pinned_cap = 0;
+  ~Workspace() {
+    frames.release(); raw.release(); counters.release(); out.release(); nout.release(); plan.release();
+    deep.release(); tiles.release(); scratch_a.release(); scratch_b.release(); scratch_c.release();
+    if (pinned) cudaFreeHost(pinned);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+struct WorkspacePool {
+  std::mutex mu;
+  std::vector<Workspace*> free_list;
+  Workspace* acquire() {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      if (!free_list.empty()) { Workspace* w = free_list.back(); free_list.pop_back(); return w; }
+    }
+    Workspace* w = new Workspace();
+    if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) { delete w; return nullptr; }
+    return w;
+  }
+  void release(Workspace* w) { std::lock_guard<std::mutex> g(mu); free_list.push_back(w); }
+  ~WorkspacePool() { for (auto* w : free_list) delete w; }
+};
+
+struct WsGuard {
+  WorkspacePool& pool; Workspace* w;
+  WsGuard(WorkspacePool& p) : pool(p), w(p.acquire()) {}
+  ~WsGuard() { if (w) pool.release(w); }
+};
+
+
+}  // namespace pigo
+
+struct pigo_cascade {
+  uint32_t depth = 0, ntrees = 0, leaves = 0;
+  pigo::DevBuf codes, preds, thresh, tiled_tab;
+  pigo::FaceTables tab{};
+  pigo::WorkspacePool pool;
+  int device = 0;
+};
+
+struct pigo_puploc {
+  pigo::PuplocTables tab{};
+  pigo::DevBuf codes, preds;
+  pigo::WorkspacePool pool;
+};
+
+
+namespace pigo {
+// kernels / drivers implemented in the other .cu files
+void launch_scan_gather(const ScanArgs& A, int grid, cudaStream_t st);
+int gather_max_ctas_per_sm(int depth, bool rot);
+void launch_finalize(const RawDet* raw, const int32_t* raw_count, int cap, const ScaleEntry* plan, int nscales, pigo_det* out,
+                     int32_t* n_out, int nframes, cudaStream_t st);
+void launch_cluster(pigo_det* dets, const int32_t* n_in, int cap, double thr, pigo_det* tmp, uint8_t* flags, int32_t* seeds,
+                    pigo_det* out, int out_cap, int32_t* n_out, int nframes, cudaStream_t st);
+void launch_puploc(const PuplocTables& T, const pigo_point* seeds, int nseeds, const float* randoms, uint64_t rng_seed,
+                   const uint8_t* pixels, int rows, int cols, int dim, int rot_slot, const uint8_t* flipv, pigo_point* out,
+                   cudaStream_t st);
+int build_tiled_tables(const FaceTables& tab, const std::vector<int8_t>& codes, const std::vector<float>& preds,
+                       const std::vector<float>& thr, DevBuf& out);
+int run_scan(pigo_cascade* c, Workspace* w, ScanArgs& A, unsigned long long* d_work, cudaStream_t st, int num_sms);
+}  // namespace pigo

@@ -1,0 +1,69 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
+include/pigo_b200.h declares, and fails LOUDLY (no CPU fallback) when no sm_100 device is present."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pigo_b200
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "pigo_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pigo_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from pigo_b200 import build
+    so = build.build()
+    assert os.path.exists(so)
+    L = pigo_b200.lib()
+    declared = _header_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/pigo_b200.h but not exported"
+    assert sorted(declared) == sorted(pigo_b200.ABI_SYMBOLS)
+    assert L.pigo_version() == 100
+
+
+def test_host_side_ladder_matches_oracle():
+    import oracle_lib as O
+    for (mn, mx, sf) in [(20, 1000, 1.1), (20, 1000, 1.15), (9, 300, 1.1), (100, 99, 1.1), (1, 50, 1.0), (24, 2000, 1.33)]:
+        assert pigo_b200.scale_ladder(mn, mx, sf) == O.scale_ladder(mn, mx, sf)
+    for (r, c, mn, mx, sh, sf) in [(1080, 1920, 20, 1000, 0.2, 1.1), (1080, 1920, 20, 1000, 0.1, 1.1),
+                                   (2160, 3840, 20, 1000, 0.2, 1.1), (400, 320, 20, 1000, 0.2, 1.1),
+                                   (480, 640, 20, 1000, 0.15, 1.15), (10, 10, 20, 1000, 0.2, 1.1), (64, 48, 8, 64, 0.0, 1.2)]:
+        assert pigo_b200.count_windows(r, c, mn, mx, sh, sf) == O.count_windows(r, c, mn, mx, sh, sf)
+    # SURVEY.md section 8(a) figures
+    assert pigo_b200.count_windows(1080, 1920, 20, 1000, 0.2, 1.1) == 894448
+    assert pigo_b200.count_windows(2160, 3840, 20, 1000, 0.2, 1.1) == 3669137
+    assert pigo_b200.count_windows(400, 320, 20, 1000, 0.2, 1.1) == 48015
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="this check is about the no-device behaviour")
+def test_no_cpu_fallback_without_device(facefinder_bytes):
+    with pytest.raises(pigo_b200.PigoError) as ei:
+        pigo_b200.NewPigo().Unpack(facefinder_bytes)
+    assert ei.value.status in (pigo_b200.PIGO_E_NODEVICE, pigo_b200.PIGO_E_CUDA)
+
+
+def test_malformed_cascade_is_rejected_before_touching_the_device():
+    with pytest.raises(pigo_b200.PigoError) as ei:
+        pigo_b200.NewPigo().Unpack(b"\x00" * 8)
+    assert ei.value.status == pigo_b200.PIGO_E_INVALID
+    bad = bytearray(pigo_b200.load_cascade("facefinder")[:1000])
+    with pytest.raises(pigo_b200.PigoError) as ei:
+        pigo_b200.NewPigo().Unpack(bytes(bad))
+    assert ei.value.status == pigo_b200.PIGO_E_INVALID

@@ -1,0 +1,238 @@
+"""GPU parity tests: libpigo_b200 (through the C-ABI, via the ctypes mirror of the Go API) against the CPU
+oracle on identical grayscale buffers.  Bar: (row, col, scale) integer-exact AND in the reference's emission
+order, Q bit-equal (float32 adds happen in tree order on both sides) -- stronger than the 1e-4 asked."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import pigo_b200
+from pigo_b200 import CascadeParams, ImageParams, Puploc, synth
+
+pytestmark = pytest.mark.gpu
+
+TEST_PARAMS = (20, 1000, 0.2, 1.1)   # core/pigo_test.go:44-50
+DOC_PARAMS = (20, 1000, 0.1, 1.1)    # README
+CLI_PARAMS = (20, 1000, 0.15, 1.15)  # cmd/pigo/main.go:110-111
+
+
+def cp_of(img, rows, cols, dim, params):
+    return CascadeParams(ImageParams(img, rows, cols, dim), params[0], params[1], params[2], params[3])
+
+
+def assert_same(gpu: np.ndarray, ora: np.ndarray):
+    assert len(gpu) == len(ora), f"{len(gpu)} detections vs oracle {len(ora)}"
+    assert gpu.tobytes() == ora.tobytes()   # row, col, scale, and the float32 bits of q, in order
+
+
+@pytest.mark.parametrize("params", [TEST_PARAMS, DOC_PARAMS, CLI_PARAMS])
+def test_sample_image(gpu_face, oracle_face, sample_gray, params, golden):
+    g = gpu_face.run_cascade_array(cp_of(sample_gray, 400, 320, 320, params), 0.0)
+    assert_same(g, oracle_face.run_cascade(sample_gray, 400, 320, 320, *params, 0.0))
+    if params == TEST_PARAMS:
+        assert g.tobytes() == golden["sample_test_dets"].tobytes()
+        # the reference's own assertion (core/pigo_test.go:68-84) through the mirrored API
+        dets = gpu_face.RunCascade(cp_of(sample_gray, 400, 320, 320, params), 0.0)
+        assert len(gpu_face.ClusterDetections(dets, 0.1)) > 0
+
+
+@pytest.mark.parametrize("k", [1, 3, 8, 13, 16, 21, 27, 31, 32, 40])
+def test_rotated_sample(gpu_face, oracle_face, sample_gray, k):
+    a = k / 32.0   # every quadrant of the table; 40/32 > 1 exercises the clamp to 1.0 (core/pigo.go:233-235)
+    g = gpu_face.run_cascade_array(cp_of(sample_gray, 400, 320, 320, TEST_PARAMS), a)
+    assert_same(g, oracle_face.run_cascade(sample_gray, 400, 320, 320, *TEST_PARAMS, a))
+
+
+def test_rotated_wide_frame_column_clamp_quirk(gpu_face, oracle_face, sample_gray):
+    """cols > rows: the reference clamps COLUMNS with nrows-1 (core/pigo.go:168,:171)."""
+    fr = synth.frame_faces(sample_gray, 300, 900, noise_seed=1)
+    for a in (0.05, 0.5, 0.97):
+        g = gpu_face.run_cascade_array(cp_of(fr, 300, 900, 900, TEST_PARAMS), a)
+        assert_same(g, oracle_face.run_cascade(fr, 300, 900, 900, *TEST_PARAMS, a))
+
+
+def test_strided_and_odd_geometry(gpu_face, oracle_face):
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, size=(97, 160), dtype=np.uint8)
+    for ang in (0.0, 0.7):
+        g = gpu_face.run_cascade_array(cp_of(img, 97, 131, 160, (12, 90, 0.1, 1.2)), ang)   # Dim != Cols (Q7)
+        assert_same(g, oracle_face.run_cascade(img, 97, 131, 160, 12, 90, 0.1, 1.2, ang))
+    patch = synth.frame_faces(None, 333, 517, shift=(11, 7))
+    buf = np.zeros((333, 531), dtype=np.uint8)
+    buf[:, :517] = patch
+    g = gpu_face.run_cascade_array(cp_of(buf, 333, 517, 531, DOC_PARAMS), 0.0)
+    o = oracle_face.run_cascade(buf, 333, 517, 531, *DOC_PARAMS, 0.0)
+    assert len(o) > 0
+    assert_same(g, o)
+
+
+def test_empty_and_degenerate_inputs(gpu_face, oracle_face):
+    tiny = np.zeros((10, 10), dtype=np.uint8)
+    assert len(gpu_face.run_cascade_array(cp_of(tiny, 10, 10, 10, TEST_PARAMS), 0.0)) == 0   # no scale fits
+    assert gpu_face.RunCascade(cp_of(tiny, 10, 10, 10, (100, 50, 0.2, 1.1)), 0.0) == []       # MinSize > MaxSize
+    one = np.random.default_rng(0).integers(0, 256, size=(21, 21), dtype=np.uint8)           # exactly one window
+    g = gpu_face.run_cascade_array(cp_of(one, 21, 21, 21, (20, 20, 0.2, 1.1)), 0.0)
+    assert_same(g, oracle_face.run_cascade(one, 21, 21, 21, 20, 20, 0.2, 1.1, 0.0))
+    assert pigo_b200.count_windows(21, 21, 20, 20, 0.2, 1.1) == 1
+    # shift factor 0 -> step 1 (core/pigo.go:227 max(...,1))
+    img = synth.frame_faces(None, 120, 100, shift=(-150, -100))
+    g = gpu_face.run_cascade_array(cp_of(img, 120, 100, 100, (30, 60, 0.0, 1.5)), 0.0)
+    assert_same(g, oracle_face.run_cascade(img, 120, 100, 100, 30, 60, 0.0, 1.5, 0.0))
+    with pytest.raises(pigo_b200.PigoError):
+        gpu_face.run_cascade_array(cp_of(img, 120, 100, 100, (0, 60, 0.1, 1.5)), 0.0)          # MinSize 0: reference would panic
+
+
+@pytest.mark.parametrize("cls", ["U", "S", "F"])
+def test_1080p_frame_each_content_class(gpu_face, oracle_face, cls):
+    fr = synth.make_batch(2, 1080, 1920, cls * 2, seed0=3)[1]
+    g = gpu_face.run_cascade_array(cp_of(fr, 1080, 1920, 1920, TEST_PARAMS), 0.0)
+    assert_same(g, oracle_face.run_cascade(fr, 1080, 1920, 1920, *TEST_PARAMS, 0.0))
+
+
+def test_1080p_golden_vector(gpu_face, golden, sample_gray):
+    f1080 = synth.frame_faces(sample_gray, 1080, 1920)
+    g = gpu_face.run_cascade_array(cp_of(f1080, 1080, 1920, 1920, TEST_PARAMS), 0.0)
+    assert g.tobytes() == golden["f1080_test_dets"].tobytes()
+    srt, cl = gpu_face.cluster_array(g, 0.2)
+    assert cl.tobytes() == golden["f1080_test_clusters"].tobytes()
+
+
+def test_batch_matches_per_frame_oracle(gpu_face, oracle_face):
+    frames = synth.make_batch(6, 540, 960, "USF", seed0=10)
+    cp = cp_of(None, 540, 960, 960, TEST_PARAMS)
+    dets, cnt = gpu_face.RunCascadeBatch(frames, cp, 0.0, cap_per_frame=256)
+    for f in range(6):
+        o = oracle_face.run_cascade(frames[f], 540, 960, 960, *TEST_PARAMS, 0.0)
+        assert cnt[f] == len(o)
+        assert dets[f, :cnt[f]].tobytes() == o.tobytes()
+
+
+def test_capacity_overflow_reports_required_count(gpu_face, oracle_face):
+    fr = synth.frame_faces(None, 1080, 1920, noise_seed=9)
+    o = oracle_face.run_cascade(fr, 1080, 1920, 1920, *TEST_PARAMS, 0.0)
+    assert len(o) > 8
+    import ctypes as C
+    out = np.zeros(4, dtype=pigo_b200.DET_DTYPE)
+    n = C.c_int()
+    rc = pigo_b200.lib().pigo_run_cascade(gpu_face._h, fr.ctypes.data, 1080, 1920, 1920, 20, 1000, 0.2, 1.1, 0.0,
+                                          out.ctypes.data, 4, C.byref(n))
+    assert rc == pigo_b200.PIGO_E_CAP and n.value == len(o)
+    assert_same(gpu_face.run_cascade_array(cp_of(fr, 1080, 1920, 1920, TEST_PARAMS), 0.0, cap=4), o)  # retry path
+
+
+def test_4k_rotated_slot(gpu_face, oracle_face):
+    """config 4 shape (3840x2160), one table slot; property: slot 32 == unrotated where no clamp bites is NOT
+    true on wide frames (column clamp quirk), so compare with the oracle only."""
+    fr = synth.frame_faces(None, 2160, 3840, shift=(5, 9), noise_seed=4)
+    for a in (7 / 32.0,):
+        g = gpu_face.run_cascade_array(cp_of(fr, 2160, 3840, 3840, TEST_PARAMS), a)
+        assert_same(g, oracle_face.run_cascade(fr, 2160, 3840, 3840, *TEST_PARAMS, a))
+    assert pigo_b200.count_windows(2160, 3840, *TEST_PARAMS) == 3669137
+
+
+# ---- ClusterDetections --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("thr", [0.0, 0.1, 0.15, 0.2, 0.5, 1.0])
+def test_cluster_matches_oracle(gpu_face, oracle_face, thr):
+    fr = synth.frame_faces(None, 1080, 1920, noise_seed=2)
+    d = oracle_face.run_cascade(fr, 1080, 1920, 1920, *DOC_PARAMS, 0.0)
+    assert len(d) > 100
+    srt_o, cl_o = O.cluster(d, thr)
+    srt_g, cl_g = gpu_face.cluster_array(d.copy(), thr)
+    assert srt_g.tobytes() == srt_o.tobytes()       # in-place sort by Q ascending (stable)
+    assert cl_g.tobytes() == cl_o.tobytes()
+
+
+def test_cluster_with_exact_score_ties(gpu_face, oracle_face, sample_gray):
+    fr = synth.frame_faces(sample_gray, 1080, 1920)   # identical tiles -> identical scores (tie order: stable)
+    d = oracle_face.run_cascade(fr, 1080, 1920, 1920, *TEST_PARAMS, 0.0)
+    qs = d["q"]
+    assert len(np.unique(qs)) < len(qs)
+    for thr in (0.0, 0.2):
+        srt_o, cl_o = O.cluster(d, thr)
+        srt_g, cl_g = gpu_face.cluster_array(d.copy(), thr)
+        assert srt_g.tobytes() == srt_o.tobytes() and cl_g.tobytes() == cl_o.tobytes()
+
+
+def test_cluster_edge_cases(gpu_face):
+    assert gpu_face.ClusterDetections([], 0.2) == []
+    one = [pigo_b200.Detection(10, 10, 20, 3.5)]
+    assert gpu_face.ClusterDetections(one, 0.2) == [pigo_b200.Detection(10, 10, 20, 3.5)]
+
+
+# ---- RunDetector / GetLandmarkPoint -------------------------------------------------------------------------
+def test_puploc_golden_cases(golden, sample_gray):
+    plc = pigo_b200.NewPuplocCascade().UnpackCascade(pigo_b200.load_cascade("puploc"))
+    img = ImageParams(sample_gray, 400, 320, 320)
+    rnd = golden["puploc_randoms"]
+    for row in golden["puploc_cases"]:
+        r0, cc, sc, P, ang, fl, o0, o1, o2 = row
+        p = plc.RunDetector(Puploc(int(r0), int(cc), float(np.float32(sc)), int(P)), img, float(ang), bool(fl), randoms=rnd)
+        assert (p.Row, p.Col) == (int(o0), int(o1)) and np.float32(p.Scale) == np.float32(o2)
+        assert p.Perturbs == 0
+
+
+def test_puploc_batch_vs_oracle_random_seeds(sample_gray):
+    pk = pigo_b200.load_cascade("puploc")
+    plc = pigo_b200.NewPuplocCascade().UnpackCascade(pk)
+    ora = O.OraclePuploc(pk)
+    rng = np.random.default_rng(99)
+    img = ImageParams(sample_gray, 400, 320, 320)
+    for ang in (0.0, 0.33):
+        seeds, flips, rnds = [], [], []
+        for k in range(40):
+            seeds.append(Puploc(int(rng.integers(-5, 405)), int(rng.integers(-5, 325)), float(np.float32(rng.uniform(5, 120))),
+                                int(rng.integers(0, 64))))
+            flips.append(bool(rng.integers(0, 2)))
+            rnds.append(rng.random(189, dtype=np.float32))
+        out = plc.run_detector_batch(seeds, img, ang, flips, np.stack(rnds))
+        for s, f, r, o in zip(seeds, flips, rnds, out):
+            e = ora.run_detector(s.Row, s.Col, s.Scale, s.Perturbs, r, sample_gray, 400, 320, 320, ang, f)
+            assert (o.Row, o.Col) == (e[0], e[1]) and np.float32(o.Scale) == e[2]
+
+
+def test_puploc_perturbs_above_63_is_rejected(sample_gray):
+    plc = pigo_b200.NewPuplocCascade().UnpackCascade(pigo_b200.load_cascade("puploc"))
+    with pytest.raises(pigo_b200.PigoError):   # the reference panics (index out of range on the 63-slot pool)
+        plc.RunDetector(Puploc(100, 100, 30.0, 64), ImageParams(sample_gray, 400, 320, 320), 0.0, False)
+
+
+def test_reference_landmark_assertion_through_the_mirror_api(gpu_face, sample_gray):
+    """core/flploc_test.go:75-154 replayed on the GPU path (library RNG): 15 points with Row>0 && Col>0."""
+    img = ImageParams(sample_gray, 400, 320, 320)
+    dets = gpu_face.RunCascade(cp_of(sample_gray, 400, 320, 320, TEST_PARAMS), 0.0)
+    dets = gpu_face.ClusterDetections(dets, 0.1)
+    plc = pigo_b200.NewPuplocCascade().UnpackCascade(pigo_b200.load_cascade("puploc"))
+    flpcs = plc.ReadCascadeDir(pigo_b200.CASCADE_DIR + "/lps")
+    n = 0
+    for det in dets:
+        if det.Scale > 50:
+            row = det.Row - int(np.float32(0.075) * np.float32(det.Scale))
+            le = plc.RunDetector(Puploc(row, det.Col - int(np.float32(0.175) * np.float32(det.Scale)),
+                                        float(np.float32(det.Scale) * np.float32(0.25)), 50), img, 0.0, False, rng_seed=1)
+            re_ = plc.RunDetector(Puploc(row, det.Col + int(np.float32(0.185) * np.float32(det.Scale)),
+                                         float(np.float32(det.Scale) * np.float32(0.25)), 50), img, 0.0, False, rng_seed=2)
+            for eye in ("lp46", "lp44", "lp42", "lp38", "lp312"):
+                for flpc in flpcs[eye]:
+                    for fl in (False, True):
+                        p = flpc.GetLandmarkPoint(le, re_, img, 63, fl, rng_seed=3)
+                        n += 1 if (p.Row > 0 and p.Col > 0) else 0
+            for mouth in ("lp93", "lp84", "lp82", "lp81"):
+                for flpc in flpcs[mouth]:
+                    p = flpc.GetLandmarkPoint(le, re_, img, 63, False, rng_seed=4)
+                    n += 1 if (p.Row > 0 and p.Col > 0) else 0
+            p = flpcs["lp84"][0].GetLandmarkPoint(le, re_, img, 63, True, rng_seed=5)
+            n += 1 if (p.Row > 0 and p.Col > 0) else 0
+    assert n == 2 * 5 + 4 + 1
+
+
+def test_get_landmark_point_vs_oracle(sample_gray):
+    pk = pigo_b200.load_cascade("lps/lp42")
+    flp = pigo_b200.NewPuplocCascade().UnpackCascade(pk)
+    ora = O.OraclePuploc(pk)
+    img = ImageParams(sample_gray, 400, 320, 320)
+    rnd = np.random.default_rng(5).random(189, dtype=np.float32)
+    le, re_ = Puploc(186, 118, 0, 0), Puploc(188, 205, 0, 0)
+    for fl in (False, True):
+        p = flp.GetLandmarkPoint(le, re_, img, 63, fl, randoms=rnd)
+        r0, c0, s0 = O.landmark_seed(le.Row, le.Col, re_.Row, re_.Col)
+        e = ora.run_detector(r0, c0, float(s0), 63, rnd, sample_gray, 400, 320, 320, 0.0, fl)
+        assert (p.Row, p.Col) == (e[0], e[1]) and np.float32(p.Scale) == e[2]
