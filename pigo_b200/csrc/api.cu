@@ -23,6 +23,55 @@ static std::atomic<int> g_device{-1};
 static int g_num_sms = 148;
 Options g_opt;
 
+// ---- per-kernel event timing --------------------------------------------------------------------------------
+struct TimingSlot {
+  std::vector<cudaEvent_t> ev;  // begin/end pairs
+  size_t used = 0;
+};
+static TimingSlot g_tslot[T_NSLOTS];
+static std::mutex g_tmu;
+static const char* kSlotNames[T_NSLOTS] = {"tiled", "gather", "deep", "finalize", "cluster", "puploc"};
+
+void timing_reset() {
+  std::lock_guard<std::mutex> g(g_tmu);
+  for (auto& s : g_tslot) s.used = 0;
+}
+static void timing_mark(int slot, cudaStream_t st) {
+  if (!g_opt.timing.load()) return;
+  std::lock_guard<std::mutex> g(g_tmu);
+  TimingSlot& s = g_tslot[slot];
+  if (s.used >= 1u << 16) return;
+  if (s.used == s.ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; }
+    s.ev.push_back(e);
+  }
+  cudaEventRecord(s.ev[s.used++], st);
+}
+void timing_begin(int slot, cudaStream_t st) { timing_mark(slot, st); }
+void timing_end(int slot, cudaStream_t st) { timing_mark(slot, st); }
+long long timing_query(const std::string& key) {
+  std::lock_guard<std::mutex> g(g_tmu);
+  for (int i = 0; i < T_NSLOTS; ++i) {
+    const std::string base = std::string("t_") + kSlotNames[i];
+    TimingSlot& s = g_tslot[i];
+    if (key == base + "_n") return (long long)(s.used / 2);
+    if (key == base + "_ns") {
+      double total = 0;
+      for (size_t k = 0; k + 1 < s.used; k += 2) {
+        float ms = 0;
+        if (cudaEventSynchronize(s.ev[k + 1]) != cudaSuccess || cudaEventElapsedTime(&ms, s.ev[k], s.ev[k + 1]) != cudaSuccess) {
+          cudaGetLastError();
+          return -2;
+        }
+        total += (double)ms * 1e6;
+      }
+      return (long long)total;
+    }
+  }
+  return -1;
+}
+
 int set_err(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -293,7 +342,9 @@ int pigo_run_cascade_batch(const pigo_cascade* cc, const uint8_t* frames, int nf
     rc = run_scan(c, w, A, d_work, st, g_num_sms);
     if (rc) return rc;
   }
+  timing_begin(T_FINALIZE, st);
   launch_finalize((const RawDet*)w->raw.p, d_rawcount, cap, (const ScaleEntry*)w->plan.p, nscales, d_out, d_nout, nframes, st);
+  timing_end(T_FINALIZE, st);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
 
@@ -357,8 +408,10 @@ int pigo_cluster_batch(pigo_det* dets, const int* n, int nframes, int cap_per_fr
     if (cap_per_frame > 0 && dets) CUDA_TRY(cudaMemcpyAsync(d_dets, dets, nd * sizeof(pigo_det), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(dn, n, (size_t)nframes * 4, cudaMemcpyHostToDevice, st));
   }
+  timing_begin(T_CLUSTER, st);
   launch_cluster(d_dets, d_n, cap, iou_threshold, (pigo_det*)w->scratch_a.p, (uint8_t*)w->scratch_b.p, (int32_t*)w->scratch_c.p,
                  d_out, ocap, d_nout, nframes, st);
+  timing_end(T_CLUSTER, st);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   if (dev) return PIGO_OK;
@@ -474,7 +527,9 @@ int pigo_puploc_run(const pigo_puploc* pc, const pigo_point* seeds, int nseeds, 
   }
   int rot_slot = -1;
   if (angle > 0.0) rot_slot = (int)(32.0 * (angle > 1.0 ? 1.0 : angle));  // core/puploc.go:252-256, :166
+  timing_begin(T_PUPLOC, st);
   launch_puploc(p->tab, d_seeds, nseeds, d_rnd, rng_seed, d_pix, rows, cols, dim, rot_slot, d_flip, d_out, st);
+  timing_end(T_PUPLOC, st);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   if (out_dev) return PIGO_OK;

@@ -14,21 +14,33 @@ namespace pigo {
 int set_err(int code, const char* fmt, ...);
 extern std::atomic<long long> g_launches;
 
+// Per-kernel CUDA-event timing (enabled by option "timing"): every launch of kernel class `slot` is bracketed by an
+// event pair on its stream; "t_<name>_ns" / "t_<name>_n" return the summed device time and the launch count.
+enum TimeSlot { T_TILED = 0, T_GATHER, T_DEEP, T_FINALIZE, T_CLUSTER, T_PUPLOC, T_NSLOTS };
+void timing_reset();
+long long timing_query(const std::string& key);
+void timing_begin(int slot, cudaStream_t st);
+void timing_end(int slot, cudaStream_t st);
+
 struct Options {
   std::atomic<long long> scan_mode{0};      // 0 auto, 1 gather only, 2 tiled + gather
   std::atomic<long long> chunk{256};        // windows per work chunk of the gather kernel
   std::atomic<long long> deep_tree{0};      // 0 = auto
   std::atomic<long long> gather_ctas_per_sm{0};
   std::atomic<long long> tile_max_scale{0}; // 0 = auto
+  std::atomic<long long> timing{0};         // 1 = bracket every kernel with CUDA events (bench.py roofline pass)
   bool set(const std::string& k, long long v) {
     if (k == "scan_mode") scan_mode = v; else if (k == "chunk") chunk = v; else if (k == "deep_tree") deep_tree = v;
     else if (k == "gather_ctas_per_sm") gather_ctas_per_sm = v; else if (k == "tile_max_scale") tile_max_scale = v;
+    else if (k == "timing") { timing = v; timing_reset(); }
     else return false;
     return true;
   }
   long long get(const std::string& k) const {
     if (k == "scan_mode") return scan_mode; if (k == "chunk") return chunk; if (k == "deep_tree") return deep_tree;
     if (k == "gather_ctas_per_sm") return gather_ctas_per_sm; if (k == "tile_max_scale") return tile_max_scale;
+    if (k == "timing") return timing;
+    if (k.rfind("t_", 0) == 0) return timing_query(k);
     return -1;
   }
 };

@@ -23,7 +23,9 @@ int run_scan(pigo_cascade* c, Workspace* w, ScanArgs& A, unsigned long long* d_w
   long long grid = (long long)num_sms * per_sm;
   const long long warps_needed = (long long)total_chunks;       // one chunk keeps a warp busy
   grid = std::max(1ll, std::min(grid, (warps_needed + 7) / 8));
+  timing_begin(T_GATHER, st);
   launch_scan_gather(A, (int)grid, st);
+  timing_end(T_GATHER, st);
   g_launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_err(PIGO_E_CUDA, "scan launch failed: %s", cudaGetErrorString(e));

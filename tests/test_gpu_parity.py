@@ -69,10 +69,11 @@ def test_empty_and_degenerate_inputs(gpu_face, oracle_face):
     tiny = np.zeros((10, 10), dtype=np.uint8)
     assert len(gpu_face.run_cascade_array(cp_of(tiny, 10, 10, 10, TEST_PARAMS), 0.0)) == 0   # no scale fits
     assert gpu_face.RunCascade(cp_of(tiny, 10, 10, 10, (100, 50, 0.2, 1.1)), 0.0) == []       # MinSize > MaxSize
-    one = np.random.default_rng(0).integers(0, 256, size=(21, 21), dtype=np.uint8)           # exactly one window
-    g = gpu_face.run_cascade_array(cp_of(one, 21, 21, 21, (20, 20, 0.2, 1.1)), 0.0)
-    assert_same(g, oracle_face.run_cascade(one, 21, 21, 21, 20, 20, 0.2, 1.1, 0.0))
-    assert pigo_b200.count_windows(21, 21, 20, 20, 0.2, 1.1) == 1
+    one = np.random.default_rng(0).integers(0, 256, size=(22, 22), dtype=np.uint8)           # exactly one window
+    g = gpu_face.run_cascade_array(cp_of(one, 22, 22, 22, (20, 20, 0.2, 1.1)), 0.0)
+    assert_same(g, oracle_face.run_cascade(one, 22, 22, 22, 20, 20, 0.2, 1.1, 0.0))
+    assert pigo_b200.count_windows(22, 22, 20, 20, 0.2, 1.1) == 1
+    assert pigo_b200.count_windows(21, 21, 20, 20, 0.2, 1.1) == 0
     # shift factor 0 -> step 1 (core/pigo.go:227 max(...,1))
     img = synth.frame_faces(None, 120, 100, shift=(-150, -100))
     g = gpu_face.run_cascade_array(cp_of(img, 120, 100, 100, (30, 60, 0.0, 1.5)), 0.0)

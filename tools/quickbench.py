@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Developer micro-benchmark (not the contract bench): times the device-resident batch scan with CUDA events."""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import pigo_b200  # noqa: E402
+from pigo_b200 import synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=32)
+    ap.add_argument("--classes", default="USF")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--opts", default="", help="comma list name=value;... variants separated by '/'")
+    ap.add_argument("--rows", type=int, default=1080)
+    ap.add_argument("--cols", type=int, default=1920)
+    ap.add_argument("--shift", type=float, default=0.2)
+    args = ap.parse_args()
+    pigo_b200.init(0)
+    clf = pigo_b200.NewPigo().Unpack(pigo_b200.load_cascade("facefinder"))
+    base = synth.make_batch(min(args.frames, 12), args.rows, args.cols, args.classes)
+    reps = -(-args.frames // len(base))
+    frames = np.concatenate([base] * reps)[:args.frames]
+    d_frames = torch.from_numpy(frames).cuda()
+    cap = 2048
+    d_out = torch.zeros((args.frames, cap, 4), dtype=torch.int32, device="cuda")
+    d_cnt = torch.zeros(args.frames, dtype=torch.int32, device="cuda")
+    W = pigo_b200.count_windows(args.rows, args.cols, 20, 1000, args.shift, 1.1)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    st = stream.cuda_stream
+    variants = [v for v in args.opts.split("/")] if args.opts else [""]
+    for v in variants:
+        for kv in filter(None, v.split(",")):
+            k, val = kv.split("=")
+            pigo_b200.set_option(k, int(val))
+
+        def run():
+            clf.run_cascade_batch_device(d_frames.data_ptr(), args.frames, args.rows * args.cols, args.rows, args.cols, args.cols,
+                                         20, 1000, args.shift, 1.1, 0.0, d_out.data_ptr(), cap, d_cnt.data_ptr(), st)
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(args.reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); run(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = float(np.median(ts))
+        print(f"[{v or 'default'}] frames={args.frames} {args.rows}x{args.cols} shift={args.shift}: {ms:.3f} ms/step  "
+              f"{args.frames * W / ms / 1e6:.1f} Mwin/s  dets={int(d_cnt.sum())} (min {min(ts):.3f} max {max(ts):.3f})", flush=True)
+
+
+if __name__ == "__main__":
+    main()
