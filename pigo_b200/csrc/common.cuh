@@ -72,6 +72,34 @@ struct ScanArgs {
   int32_t deep_tree;  // hand over to the deep kernel when an item reaches this tree (>= ntrees: never)
 };
 
+// ---- tiled kernel -------------------------------------------------------------------------------------------
+constexpr int kTiledMaxThreads = 512;
+constexpr int kMaxBands = 4;
+
+// A band = consecutive ladder entries [scale_lo, scale_lo+nscales) served by one family of pixel tiles.
+struct TileBand {
+  int32_t scale_lo, nscales;   // <= 32 scales per band (one lane describes one scale)
+  int32_t halo_lo;             // pixels needed above/left of a window centre:  ceil(s_max/2)
+  int32_t core;                // core edge: a tile owns the windows whose centre lies in its core square
+  int32_t org_x;               // x of the first core column; org_x - halo_lo is a multiple of 16
+  int32_t tiles_x, ntiles;     // tiles per row / per frame
+  int32_t pitch;               // shared-memory row pitch in bytes (multiple of 16)
+  int32_t rows_t;              // tile rows: halo_lo + core + halo_hi
+  int32_t pad;
+};
+
+struct TiledArgs {
+  ScanArgs scan;
+  const uint8_t* tab_tiled;    // [ntrees] records of 516 bytes: 256 codes (node idx at byte 4*idx), 64 f32 leaves, f32 threshold
+  int32_t ks;                  // trees resident in shared memory
+  uint32_t tile_bytes;         // per-warp tile buffer
+  int32_t nbands;
+  int32_t tail_min;            // after a tile is drained, slot groups with fewer live items are handed to the deep queue
+  TileBand band[kMaxBands];
+  uint32_t tiles_per_frame;
+  unsigned long long total_tiles;
+};
+
 __device__ __constant__ int c_qcos[33] = {256, 251, 236, 212, 181, 142, 97, 49, 0, -49, -97, -142, -181, -212, -236, -251, -256,
                                           -251, -236, -212, -181, -142, -97, -49, 0, 49, 97, 142, 181, 212, 236, 251, 256};
 __device__ __constant__ int c_qsin[33] = {0, 49, 97, 142, 181, 212, 236, 251, 256, 251, 236, 212, 181, 142, 97, 49, 0,

@@ -27,12 +27,19 @@ struct Options {
   std::atomic<long long> chunk{256};        // windows per work chunk of the gather kernel
   std::atomic<long long> deep_tree{0};      // 0 = auto
   std::atomic<long long> gather_ctas_per_sm{0};
-  std::atomic<long long> tile_max_scale{0}; // 0 = auto
+  std::atomic<long long> tile_max_scale{0}; // largest window size routed to the tiled kernel (0 = auto)
+  std::atomic<long long> tile_warps{8};     // warps (= private tile buffers) per CTA of the tiled kernel
+  std::atomic<long long> tile_ni{2};        // item slots per lane
+  std::atomic<long long> tile_ks{64};       // cascade trees resident in shared memory
+  std::atomic<long long> tile_tail_min{8};  // tail policy threshold
+  std::atomic<long long> tile_band_ratio{200};  // a band spans scales up to ratio/100 x its first scale
   std::atomic<long long> timing{0};         // 1 = bracket every kernel with CUDA events (bench.py roofline pass)
   bool set(const std::string& k, long long v) {
     if (k == "scan_mode") scan_mode = v; else if (k == "chunk") chunk = v; else if (k == "deep_tree") deep_tree = v;
     else if (k == "gather_ctas_per_sm") gather_ctas_per_sm = v; else if (k == "tile_max_scale") tile_max_scale = v;
     else if (k == "timing") { timing = v; timing_reset(); }
+    else if (k == "tile_warps") tile_warps = v; else if (k == "tile_ni") tile_ni = v; else if (k == "tile_ks") tile_ks = v;
+    else if (k == "tile_tail_min") tile_tail_min = v; else if (k == "tile_band_ratio") tile_band_ratio = v;
     else return false;
     return true;
   }
@@ -40,6 +47,8 @@ struct Options {
     if (k == "scan_mode") return scan_mode; if (k == "chunk") return chunk; if (k == "deep_tree") return deep_tree;
     if (k == "gather_ctas_per_sm") return gather_ctas_per_sm; if (k == "tile_max_scale") return tile_max_scale;
     if (k == "timing") return timing;
+    if (k == "tile_warps") return tile_warps; if (k == "tile_ni") return tile_ni; if (k == "tile_ks") return tile_ks;
+    if (k == "tile_tail_min") return tile_tail_min; if (k == "tile_band_ratio") return tile_band_ratio;
     if (k.rfind("t_", 0) == 0) return timing_query(k);
     return -1;
   }
@@ -134,6 +143,8 @@ struct pigo_puploc {
 namespace pigo {
 // kernels / drivers implemented in the other .cu files
 void launch_scan_gather(const ScanArgs& A, int grid, cudaStream_t st);
+void launch_scan_resume(const ScanArgs& A, int grid, cudaStream_t st);
+void launch_scan_tiled(const TiledArgs& A, int grid, int threads, size_t smem, int ni, bool aligned, cudaStream_t st);
 int gather_max_ctas_per_sm(int depth, bool rot);
 void launch_finalize(const RawDet* raw, const int32_t* raw_count, int cap, const ScaleEntry* plan, int nscales, pigo_det* out,
                      int32_t* n_out, int nframes, cudaStream_t st);
