@@ -291,6 +291,7 @@ int pigo_run_cascade_batch(const pigo_cascade* cc, const uint8_t* frames, int nf
     if (!w->plan_host.empty())
       CUDA_TRY(cudaMemcpyAsync(w->plan.p, w->plan_host.data(), w->plan_host.size() * sizeof(ScaleEntry), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));  // plan_host may be rebuilt by the next call before the copy ran
+    w->pad_first_untiled = -1;
     w->p_rows = rows; w->p_cols = cols; w->p_min = min_size; w->p_max = max_size; w->p_shift = shift_factor; w->p_scale = scale_factor;
   }
   const int nscales = (int)w->plan_host.size();
@@ -301,15 +302,8 @@ int pigo_run_cascade_batch(const pigo_cascade* cc, const uint8_t* frames, int nf
   const size_t frame_bytes = (size_t)rows * dim;
   size_t d_stride = frame_stride;
   if (!frames_dev) {
-    // last frame may be shorter than the stride in the caller's buffer: copy frame by frame when strided
     d_stride = (frame_bytes + 255) & ~(size_t)255;
     if ((rc = w->frames.reserve(d_stride * nframes + 256))) return rc;
-    if (frame_stride == d_stride || nframes == 1) {
-      CUDA_TRY(cudaMemcpyAsync(w->frames.p, frames, nframes == 1 ? frame_bytes : d_stride * (nframes - 1) + frame_bytes,
-                               cudaMemcpyHostToDevice, st));
-    } else {
-      CUDA_TRY(cudaMemcpy2DAsync(w->frames.p, d_stride, frames, frame_stride, frame_bytes, nframes, cudaMemcpyHostToDevice, st));
-    }
     d_frames = (const uint8_t*)w->frames.p;
   }
   pigo_det* d_out = out;
@@ -321,26 +315,64 @@ int pigo_run_cascade_batch(const pigo_cascade* cc, const uint8_t* frames, int nf
     d_nout = (int32_t*)w->nout.p;
   }
   if ((rc = w->raw.reserve((size_t)nframes * cap * sizeof(RawDet)))) return rc;
-  // counters: [0..nframes) raw counts | 8 x u64 work counters | deep count
-  const size_t cnt_bytes = (size_t)nframes * 4 + 256;
+
+  // Sub-batch pipeline: the batch is cut into groups of `sub_batch` frames that alternate between `lanes` internal
+  // streams.  (1) The deferred queues (Q1/Q2) of a group are consumed while its frames are still L2-resident;
+  // (2) the tail kernels of one group overlap the bulk kernels of the next; (3) with host frames, the H2D copy of
+  // group k+1 overlaps the scan of group k.
+  int sub = (int)g_opt.sub_batch.load();
+  if (sub <= 0 || sub > nframes) sub = nframes;
+  const int nsub = (nframes + sub - 1) / sub;
+  int lanes = (int)std::min<long long>(std::max<long long>(1, g_opt.lanes.load()), kMaxLanes);
+  if (nsub == 1) lanes = 1;
+  if ((rc = w->ensure_lanes(lanes))) return rc;
+
+  // counters: [0..nframes) raw counts | 8 x u64 work counters per sub-batch
+  const size_t work_off = ((size_t)nframes * 4 + 15) & ~(size_t)15;
+  const size_t cnt_bytes = work_off + (size_t)nsub * 64 + 64;
   if ((rc = w->counters.reserve(cnt_bytes))) return rc;
   CUDA_TRY(cudaMemsetAsync(w->counters.p, 0, cnt_bytes, st));
   int32_t* d_rawcount = (int32_t*)w->counters.p;
-  unsigned long long* d_work = (unsigned long long*)((char*)w->counters.p + (((size_t)nframes * 4 + 15) & ~(size_t)15));
+  unsigned long long* d_work = (unsigned long long*)((char*)w->counters.p + work_off);
 
-  if (nscales > 0 && c->ntrees > 0) {
-    ScanArgs A{};
-    A.tab = c->tab;
-    A.frames = d_frames; A.frame_stride = d_stride; A.nframes = nframes; A.rows = rows; A.cols = cols; A.dim = dim;
-    A.plan = (const ScaleEntry*)w->plan.p; A.nscales = nscales; A.wins_per_frame = (uint32_t)w->wins;
-    A.rot_slot = -1;
-    if (angle > 0.0) {                      // core/pigo.go:232-236
-      const double a = angle > 1.0 ? 1.0 : angle;
-      A.rot_slot = (int)(32.0 * a);         // :159
+  if (lanes > 1) {
+    CUDA_TRY(cudaEventRecord(w->ev_fork, st));
+    for (int l = 0; l < lanes; ++l) CUDA_TRY(cudaStreamWaitEvent(w->lane_stream[l], w->ev_fork, 0));
+  }
+  int rot_slot = -1;
+  if (angle > 0.0) {                      // core/pigo.go:232-236
+    const double a = angle > 1.0 ? 1.0 : angle;
+    rot_slot = (int)(32.0 * a);           // :159
+  }
+  for (int k = 0; k < nsub; ++k) {
+    const int f0 = k * sub, nf = std::min(sub, nframes - f0);
+    const int lane = k % lanes;
+    cudaStream_t ls = lanes > 1 ? w->lane_stream[lane] : st;
+    if (!frames_dev) {
+      uint8_t* dst = (uint8_t*)w->frames.p + (size_t)f0 * d_stride;
+      const uint8_t* src = frames + (size_t)f0 * frame_stride;
+      if (frame_stride == d_stride || nf == 1) {
+        CUDA_TRY(cudaMemcpyAsync(dst, src, nf == 1 ? frame_bytes : d_stride * (nf - 1) + frame_bytes, cudaMemcpyHostToDevice, ls));
+      } else {
+        CUDA_TRY(cudaMemcpy2DAsync(dst, d_stride, src, frame_stride, frame_bytes, nf, cudaMemcpyHostToDevice, ls));
+      }
     }
-    A.raw = (RawDet*)w->raw.p; A.raw_count = d_rawcount; A.cap = cap;
-    rc = run_scan(c, w, A, d_work, st, g_num_sms);
-    if (rc) return rc;
+    if (nscales > 0 && c->ntrees > 0) {
+      ScanArgs A{};
+      A.tab = c->tab;
+      A.frames = d_frames + (size_t)f0 * d_stride; A.frame_stride = d_stride; A.nframes = nf; A.rows = rows; A.cols = cols; A.dim = dim;
+      A.plan = (const ScaleEntry*)w->plan.p; A.nscales = nscales; A.wins_per_frame = (uint32_t)w->wins;
+      A.rot_slot = rot_slot;
+      A.raw = (RawDet*)w->raw.p + (size_t)f0 * cap; A.raw_count = d_rawcount + f0; A.cap = cap;
+      rc = run_scan(c, w, lane, A, d_work + 8 * (size_t)k, ls, g_num_sms);
+      if (rc) return rc;
+    }
+  }
+  if (lanes > 1) {
+    for (int l = 0; l < lanes; ++l) {
+      CUDA_TRY(cudaEventRecord(w->ev_join[l], w->lane_stream[l]));
+      CUDA_TRY(cudaStreamWaitEvent(st, w->ev_join[l], 0));
+    }
   }
   timing_begin(T_FINALIZE, st);
   launch_finalize((const RawDet*)w->raw.p, d_rawcount, cap, (const ScaleEntry*)w->plan.p, nscales, d_out, d_nout, nframes, st);

@@ -17,7 +17,7 @@ struct ScaleEntry {
   int32_t ncols;    // grid cols
   uint32_t wbase;   // index of this scale's first window in the frame's emission order
   uint32_t nwin;    // nrows*ncols
-  uint32_t pad;
+  uint32_t pad;     // gather role: index of this scale's first 16x16-window block among the gather scales
 };
 
 // Face cascade tables on the device.  `codes` keeps the reference's in-memory layout
@@ -65,15 +65,22 @@ struct ScanArgs {
   uint32_t chunks_per_frame;
   // gather-kernel window filter: only scales with index in [scale_lo, scale_hi) (tiled kernel takes the rest)
   int32_t scale_lo, scale_hi;
-  // deep queue (optional)
+  // Q1 "straggler" queue (optional): windows still alive when a tile warp drained its tile; any tree index.
+  // Consumed one-item-per-lane by the gather-v2 kernel.
   DeepItem* deep;
   unsigned int* deep_count;
   uint32_t deep_cap;
-  int32_t deep_tree;  // hand over to the deep kernel when an item reaches this tree (>= ntrees: never)
+  int32_t deep_tree;  // unused by the current kernels (kept for the standalone gather kernel's ABI)
+  // Q2 "long" queue: windows that survived the KS shared-memory-resident trees.  Consumed one-item-per-WARP
+  // (32 trees evaluated in parallel) by the deep kernel, which bounds the serial chain of a full survivor.
+  DeepItem* longq;
+  unsigned int* long_count;
+  uint32_t long_cap;
+  uint32_t pad2;
 };
 
 // ---- tiled kernel -------------------------------------------------------------------------------------------
-constexpr int kTiledMaxThreads = 512;
+constexpr int kTiledMaxThreads = 1024;
 constexpr int kMaxBands = 4;
 
 // A band = consecutive ladder entries [scale_lo, scale_lo+nscales) served by one family of pixel tiles.
@@ -94,10 +101,19 @@ struct TiledArgs {
   int32_t ks;                  // trees resident in shared memory
   uint32_t tile_bytes;         // per-warp tile buffer
   int32_t nbands;
+  int32_t aligned;             // frames, stride and Dim are 16-byte aligned: tiles are filled with cp.async 16 B
   int32_t tail_min;            // after a tile is drained, slot groups with fewer live items are handed to the deep queue
   TileBand band[kMaxBands];
   uint32_t tiles_per_frame;
   unsigned long long total_tiles;
+  // warp specialisation inside the fused kernel
+  int32_t tile_warps;                     // warps [0, tile_warps) own pixel tiles; the rest gather
+  int32_t gather_scale_lo;                // first ladder entry scanned by the gather warps
+  uint32_t gather_blocks_per_frame;       // 16x16-window blocks of those scales (ScaleEntry.pad = block prefix)
+  unsigned long long* gather_counter;
+  unsigned long long* q1_counter;         // consumer cursor of Q1 (gather-v2 kernel only)
+  int32_t consume_q1;
+  int32_t gather_ni;                      // windows per lane in the gather role (ILP)
 };
 
 __device__ __constant__ int c_qcos[33] = {256, 251, 236, 212, 181, 142, 97, 49, 0, -49, -97, -142, -181, -212, -236, -251, -256,

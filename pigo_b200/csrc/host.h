@@ -28,9 +28,15 @@ struct Options {
   std::atomic<long long> deep_tree{0};      // 0 = auto
   std::atomic<long long> gather_ctas_per_sm{0};
   std::atomic<long long> tile_max_scale{0}; // largest window size routed to the tiled kernel (0 = auto)
-  std::atomic<long long> tile_warps{8};     // warps (= private tile buffers) per CTA of the tiled kernel
-  std::atomic<long long> tile_ni{2};        // item slots per lane
-  std::atomic<long long> tile_ks{64};       // cascade trees resident in shared memory
+  std::atomic<long long> tile_warps{16};    // warps (= private tile buffers) per CTA of the tiled kernel
+  std::atomic<long long> tile_ni{1};        // item slots per lane
+  std::atomic<long long> gather_warps{16};  // gather-role warps per CTA of the fused kernel (0 = separate gather launch)
+  std::atomic<long long> tile_ks{64};       // cascade trees resident in shared memory (fused kernel)
+  std::atomic<long long> gather_ks{32};     // cascade trees resident in shared memory (gather-v2 kernel)
+  std::atomic<long long> gather_ni{1};      // windows per lane in the gather role / gather-v2 kernel
+  std::atomic<long long> deep_smem{0};      // 1: deep kernel keeps the cascade tail in shared memory (32 warps/SM) instead of L2
+  std::atomic<long long> sub_batch{32};     // frames per pipeline group (0 = whole batch)
+  std::atomic<long long> lanes{1};          // internal streams the groups alternate between      // deep kernel keeps the cascade tail in shared memory when it fits
   std::atomic<long long> tile_tail_min{8};  // tail policy threshold
   std::atomic<long long> tile_band_ratio{200};  // a band spans scales up to ratio/100 x its first scale
   std::atomic<long long> timing{0};         // 1 = bracket every kernel with CUDA events (bench.py roofline pass)
@@ -38,6 +44,7 @@ struct Options {
     if (k == "scan_mode") scan_mode = v; else if (k == "chunk") chunk = v; else if (k == "deep_tree") deep_tree = v;
     else if (k == "gather_ctas_per_sm") gather_ctas_per_sm = v; else if (k == "tile_max_scale") tile_max_scale = v;
     else if (k == "timing") { timing = v; timing_reset(); }
+    else if (k == "gather_warps") gather_warps = v; else if (k == "gather_ks") gather_ks = v; else if (k == "deep_smem") deep_smem = v; else if (k == "gather_ni") gather_ni = v; else if (k == "sub_batch") sub_batch = v; else if (k == "lanes") lanes = v;
     else if (k == "tile_warps") tile_warps = v; else if (k == "tile_ni") tile_ni = v; else if (k == "tile_ks") tile_ks = v;
     else if (k == "tile_tail_min") tile_tail_min = v; else if (k == "tile_band_ratio") tile_band_ratio = v;
     else return false;
@@ -47,6 +54,7 @@ struct Options {
     if (k == "scan_mode") return scan_mode; if (k == "chunk") return chunk; if (k == "deep_tree") return deep_tree;
     if (k == "gather_ctas_per_sm") return gather_ctas_per_sm; if (k == "tile_max_scale") return tile_max_scale;
     if (k == "timing") return timing;
+    if (k == "gather_warps") return gather_warps; if (k == "gather_ks") return gather_ks; if (k == "deep_smem") return deep_smem; if (k == "gather_ni") return gather_ni; if (k == "sub_batch") return sub_batch; if (k == "lanes") return lanes;
     if (k == "tile_warps") return tile_warps; if (k == "tile_ni") return tile_ni; if (k == "tile_ks") return tile_ks;
     if (k == "tile_tail_min") return tile_tail_min; if (k == "tile_band_ratio") return tile_band_ratio;
     if (k.rfind("t_", 0) == 0) return timing_query(k);
@@ -82,19 +90,41 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+constexpr int kMaxLanes = 4;
+
 struct Workspace {
   cudaStream_t stream = nullptr;
-  DevBuf frames, raw, counters, out, nout, plan, deep, tiles, scratch_a, scratch_b, scratch_c;
+  DevBuf frames, raw, counters, out, nout, plan, tiles, scratch_a, scratch_b, scratch_c;
+  DevBuf deep[kMaxLanes], longq[kMaxLanes];   // Q1 / Q2 per pipeline lane
+  cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  int ensure_lanes(int n) {
+    if (!ev_fork && cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess) return set_err(PIGO_E_CUDA, "event creation failed");
+    for (int l = 0; l < n && n > 1; ++l) {
+      if (!lane_stream[l] && cudaStreamCreateWithFlags(&lane_stream[l], cudaStreamNonBlocking) != cudaSuccess)
+        return set_err(PIGO_E_CUDA, "stream creation failed");
+      if (!ev_join[l] && cudaEventCreateWithFlags(&ev_join[l], cudaEventDisableTiming) != cudaSuccess)
+        return set_err(PIGO_E_CUDA, "event creation failed");
+    }
+    return PIGO_OK;
+  }
   // cached plan
   std::vector<ScaleEntry> plan_host;
   uint64_t wins = 0;
   int p_rows = -1, p_cols = -1, p_min = 0, p_max = 0;
+  int pad_first_untiled = -1;  // which gather-block prefix is currently stored in the device copy of the plan
   double p_shift = 0, p_scale = 0;
   void* pinned = nullptr;
   size_t pinned_cap = 0;
   ~Workspace() {
     frames.release(); raw.release(); counters.release(); out.release(); nout.release(); plan.release();
-    deep.release(); tiles.release(); scratch_a.release(); scratch_b.release(); scratch_c.release();
+    for (int l = 0; l < kMaxLanes; ++l) {
+      deep[l].release(); longq[l].release();
+      if (lane_stream[l]) cudaStreamDestroy(lane_stream[l]);
+      if (ev_join[l]) cudaEventDestroy(ev_join[l]);
+    }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    tiles.release(); scratch_a.release(); scratch_b.release(); scratch_c.release();
     if (pinned) cudaFreeHost(pinned);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -144,7 +174,12 @@ namespace pigo {
 // kernels / drivers implemented in the other .cu files
 void launch_scan_gather(const ScanArgs& A, int grid, cudaStream_t st);
 void launch_scan_resume(const ScanArgs& A, int grid, cudaStream_t st);
-void launch_scan_tiled(const TiledArgs& A, int grid, int threads, size_t smem, int ni, bool aligned, cudaStream_t st);
+void launch_scan_tiled(const TiledArgs& A, int grid, int threads, size_t smem, int ni, cudaStream_t st);
+int tiled_max_threads(int ni);
+void launch_scan_gather2(const TiledArgs& A, int grid, size_t smem, cudaStream_t st);
+int gather2_ctas_per_sm(size_t smem);
+void launch_deep(const ScanArgs& A, unsigned long long* counter, int grid, cudaStream_t st);
+void launch_deep_smem(const ScanArgs& A, unsigned long long* counter, const uint8_t* tab_tiled, int kd, int grid, cudaStream_t st);
 int gather_max_ctas_per_sm(int depth, bool rot);
 void launch_finalize(const RawDet* raw, const int32_t* raw_count, int cap, const ScaleEntry* plan, int nscales, pigo_det* out,
                      int32_t* n_out, int nframes, cudaStream_t st);
@@ -155,5 +190,5 @@ void launch_puploc(const PuplocTables& T, const pigo_point* seeds, int nseeds, c
                    cudaStream_t st);
 int build_tiled_tables(const FaceTables& tab, const std::vector<int8_t>& codes, const std::vector<float>& preds,
                        const std::vector<float>& thr, DevBuf& out);
-int run_scan(pigo_cascade* c, Workspace* w, ScanArgs& A, unsigned long long* d_work, cudaStream_t st, int num_sms);
+int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long long* d_work, cudaStream_t st, int num_sms);
 }  // namespace pigo

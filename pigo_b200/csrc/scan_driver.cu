@@ -17,7 +17,7 @@ int build_tiled_tables(const FaceTables& tab, const std::vector<int8_t>& codes, 
                        const std::vector<float>& thr, DevBuf& out) {
   if (tab.depth != 6) return PIGO_OK;  // other depths use the gather kernel only
   const size_t n = (size_t)tab.ntrees;
-  std::vector<uint8_t> rec(n * 516 + 64, 0);
+  std::vector<uint8_t> rec(n * 516 + 64, 0);   // 64 spare bytes: the prefix copy is rounded up to 16 bytes
   for (size_t t = 0; t < n; ++t) {
     memcpy(rec.data() + t * 516, codes.data() + t * 256, 256);
     memcpy(rec.data() + t * 516 + 256, preds.data() + t * 64, 256);
@@ -90,94 +90,165 @@ static TilePlan plan_bands(const std::vector<ScaleEntry>& plan, uint32_t tile_by
   return tp;
 }
 
+// Stores the prefix of 16x16-window blocks of the ladder entries [lo, hi) in ScaleEntry.pad and refreshes the device copy.
+static int upload_block_prefix(Workspace* w, int lo, int hi, cudaStream_t st, uint32_t* blocks_per_frame) {
+  uint32_t nb = 0;
+  for (int i = lo; i < hi; ++i) {
+    ScaleEntry& e = w->plan_host[i];
+    e.pad = nb;
+    nb += (uint32_t)((e.ncols + 15) / 16) * (uint32_t)((e.nrows + 15) / 16);
+  }
+  *blocks_per_frame = nb;
+  if (w->pad_first_untiled != lo) {
+    if (cudaMemcpyAsync(w->plan.p, w->plan_host.data(), w->plan_host.size() * sizeof(ScaleEntry), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess)
+      return set_err(PIGO_E_CUDA, "plan upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    w->pad_first_untiled = lo;
+  }
+  return PIGO_OK;
+}
+
 static int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_err(PIGO_E_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
   return PIGO_OK;
 }
 
-int run_scan(pigo_cascade* c, Workspace* w, ScanArgs& A, unsigned long long* d_work, cudaStream_t st, int num_sms) {
+int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long long* d_work, cudaStream_t st, int num_sms) {
   int rc;
   const bool rot = A.rot_slot >= 0;
   const long long mode = g_opt.scan_mode.load();
-  A.deep = nullptr; A.deep_count = (unsigned int*)(d_work + 3); A.deep_cap = 0; A.deep_tree = 0x7fffffff;
+  // d_work (zeroed per call): [0] gather block cursor  [1] tile cursor  [2] Q1 consumer cursor  [3] Q2 consumer cursor
+  //                           [4] Q1 count (u32)       [5] Q2 count (u32)  [6] chunk cursor of the standalone gather kernel
+  A.deep = nullptr; A.deep_count = (unsigned int*)(d_work + 4); A.deep_cap = 0; A.deep_tree = 0x7fffffff;
+  A.longq = nullptr; A.long_count = (unsigned int*)(d_work + 5); A.long_cap = 0;
   A.chunk = (uint32_t)std::max<long long>(32, g_opt.chunk.load());
+  A.chunk_counter = d_work + 6;
 
-  // ---- tiled kernel over the small/medium scales
-  int first_gather_scale = 0;
-  const bool can_tile = !rot && A.tab.depth == 6 && c->tiled_tab.p != nullptr && mode != 1;
-  if (can_tile) {
-    const int W = (int)std::min<long long>(std::max<long long>(1, g_opt.tile_warps.load()), kTiledMaxThreads / 32);
-    int ks = (int)std::min<long long>(std::max<long long>(4, g_opt.tile_ks.load()), A.tab.ntrees);
-    ks &= ~3;
-    if (ks < 4) ks = A.tab.ntrees;  // tiny cascades: everything resident (record size keeps 16-byte multiples only for ks%4==0)
-    const int ni = (int)std::min<long long>(std::max<long long>(1, g_opt.tile_ni.load()), 4);
-    const size_t casc_bytes = (size_t)ks * 516;
-    const size_t tiles0 = (16 + casc_bytes + 127) & ~(size_t)127;
-    if (tiles0 + 4096 * (size_t)W < kSmemPerCta && casc_bytes % 16 == 0) {
+  const bool fast = !rot && A.tab.depth == 6 && c->tiled_tab.p != nullptr && mode != 1;
+  if (!fast) {
+    // ---- universal path: standalone gather kernel over every scale (rotated path, other depths, scan_mode=1)
+    ScanArgs G = A;
+    G.scale_lo = 0; G.scale_hi = A.nscales;
+    G.chunks_per_frame = (A.wins_per_frame + G.chunk - 1) / G.chunk;
+    int per_sm = (int)g_opt.gather_ctas_per_sm.load();
+    if (per_sm <= 0) per_sm = gather_max_ctas_per_sm(A.tab.depth, rot);
+    const unsigned long long total_chunks = (unsigned long long)G.chunks_per_frame * A.nframes;
+    const long long grid = std::max(1ll, std::min<long long>((long long)num_sms * per_sm, (long long)((total_chunks + 7) / 8)));
+    timing_begin(T_GATHER, st);
+    launch_scan_gather(G, (int)grid, st);
+    timing_end(T_GATHER, st);
+    g_launches++;
+    return check_launch("gather scan");
+  }
+
+  // ---- queues
+  const uint64_t total_windows = (uint64_t)A.wins_per_frame * A.nframes;
+  const uint64_t q1_cap = std::min<uint64_t>(total_windows / 16 + 65536, 1ull << 26);
+  const uint64_t q2_cap = std::min<uint64_t>(total_windows / 32 + 65536, 1ull << 26);
+  if ((rc = w->deep[lane].reserve(q1_cap * sizeof(DeepItem)))) return rc;
+  if ((rc = w->longq[lane].reserve(q2_cap * sizeof(DeepItem)))) return rc;
+  A.deep = (DeepItem*)w->deep[lane].p; A.deep_cap = (uint32_t)q1_cap;
+  A.longq = (DeepItem*)w->longq[lane].p; A.long_cap = (uint32_t)q2_cap;
+
+  TiledArgs T{};
+  T.scan = A;
+  T.scan.chunk_counter = d_work + 1;
+  T.tab_tiled = (const uint8_t*)c->tiled_tab.p;
+  T.gather_counter = d_work;
+  T.q1_counter = d_work + 2;
+  T.gather_scale_lo = 0;
+  T.gather_blocks_per_frame = 0;
+  T.gather_ni = (int)std::min<long long>(std::max<long long>(1, g_opt.gather_ni.load()), 3);
+
+  // ---- fused kernel: tile warps over the small scales (+ optional gather warps over the rest)
+  const int ni = (int)std::min<long long>(std::max<long long>(1, g_opt.tile_ni.load()), 4);
+  const int max_warps = tiled_max_threads(ni) / 32;
+  const int W = (int)std::min<long long>(std::max<long long>(0, g_opt.tile_warps.load()), max_warps);
+  int Wg = (int)std::min<long long>(std::max<long long>(0, g_opt.gather_warps.load()), max_warps - W);
+  auto round_ks = [&](long long v) {
+    const long long fit = (long long)((kSmemPerCta - 512) / 516);   // what one CTA's shared memory can hold at most
+    return (int)std::min<long long>(std::min<long long>(std::max<long long>(1, v), A.tab.ntrees), fit);
+  };
+  int first_untiled = 0;
+  int min_handover_tree = A.tab.ntrees;
+  bool blocks_done = false, tiled_ran = false;
+  if (W > 0 && mode != 3) {
+    const int ks = round_ks(g_opt.tile_ks.load());
+    const size_t casc_bytes = ((size_t)ks * 516 + 15) & ~(size_t)15;   // TMA bulk copies move multiples of 16 bytes
+    const size_t tiles0 = (384 + casc_bytes + 127) & ~(size_t)127;
+    if (tiles0 + 4096 * (size_t)W < kSmemPerCta) {
       const uint32_t tile_bytes = (uint32_t)(((kSmemPerCta - tiles0) / W) & ~(size_t)127);
       int max_scale = (int)g_opt.tile_max_scale.load();
       if (max_scale <= 0) max_scale = 1 << 30;
       const TilePlan tp = plan_bands(w->plan_host, tile_bytes, max_scale, (int)std::max<long long>(100, g_opt.tile_band_ratio.load()));
       if (tp.nbands > 0) {
-        const uint64_t total_windows = (uint64_t)A.wins_per_frame * A.nframes;
-        uint64_t deep_cap = std::min<uint64_t>(total_windows / 12 + 65536, 1ull << 26);
-        if ((rc = w->deep.reserve(deep_cap * sizeof(DeepItem)))) return rc;
-        TiledArgs T{};
-        T.scan = A;
-        T.scan.deep = (DeepItem*)w->deep.p; T.scan.deep_cap = (uint32_t)deep_cap;
-        T.scan.chunk_counter = d_work + 1;
-        T.tab_tiled = (const uint8_t*)c->tiled_tab.p;
-        T.ks = ks; T.tile_bytes = tile_bytes; T.nbands = tp.nbands;
-        T.tail_min = (int)g_opt.tile_tail_min.load();
-        for (int b = 0; b < tp.nbands; ++b) T.band[b] = tp.band[b];
-        T.tiles_per_frame = tp.tiles_per_frame;
-        T.total_tiles = (unsigned long long)tp.tiles_per_frame * A.nframes;
-        const bool aligned = (A.dim % 16 == 0) && (A.frame_stride % 16 == 0) && (((uintptr_t)A.frames) % 16 == 0);
-        const long long grid = std::max<long long>(1, std::min<long long>(num_sms, (long long)((T.total_tiles + W - 1) / W)));
+        TiledArgs F = T;
+        F.ks = ks; F.tile_bytes = tile_bytes; F.nbands = tp.nbands;
+        F.tail_min = (int)g_opt.tile_tail_min.load();
+        for (int b = 0; b < tp.nbands; ++b) F.band[b] = tp.band[b];
+        F.tiles_per_frame = tp.tiles_per_frame;
+        F.total_tiles = (unsigned long long)tp.tiles_per_frame * A.nframes;
+        F.tile_warps = W;
+        F.consume_q1 = 0;
+        first_untiled = tp.first_untiled;
+        if (Wg > 0 && first_untiled < A.nscales) {
+          if ((rc = upload_block_prefix(w, first_untiled, A.nscales, st, &F.gather_blocks_per_frame))) return rc;
+          F.gather_scale_lo = first_untiled;
+          blocks_done = true;
+        } else {
+          Wg = 0;
+        }
+        F.aligned = ((A.dim % 16 == 0) && (A.frame_stride % 16 == 0) && (((uintptr_t)A.frames) % 16 == 0)) ? 1 : 0;
+        long long grid = num_sms;
+        if (Wg == 0) grid = std::max<long long>(1, std::min<long long>(num_sms, (long long)((F.total_tiles + W - 1) / W)));
         const size_t smem = tiles0 + (size_t)tile_bytes * W;
         timing_begin(T_TILED, st);
-        launch_scan_tiled(T, (int)grid, W * 32, smem, ni, aligned, st);
+        launch_scan_tiled(F, (int)grid, (W + Wg) * 32, smem, ni, st);
         timing_end(T_TILED, st);
         g_launches++;
-        if ((rc = check_launch("tiled scan"))) return rc;
-        first_gather_scale = tp.first_untiled;
-        A.deep = T.scan.deep; A.deep_cap = T.scan.deep_cap;
+        if ((rc = check_launch("fused scan"))) return rc;
+        tiled_ran = true;
+        min_handover_tree = std::min(min_handover_tree, ks);
       }
     }
   }
 
-  // ---- gather kernel over whatever is left
-  if (first_gather_scale < A.nscales) {
-    ScanArgs G = A;
-    G.scale_lo = first_gather_scale; G.scale_hi = A.nscales;
-    const uint32_t w_lo = w->plan_host[first_gather_scale].wbase;
-    const uint32_t span = A.wins_per_frame - w_lo;
-    G.chunks_per_frame = (span + G.chunk - 1) / G.chunk;
-    G.chunk_counter = d_work;
-    int per_sm = (int)g_opt.gather_ctas_per_sm.load();
-    if (per_sm <= 0) per_sm = gather_max_ctas_per_sm(A.tab.depth, rot);
-    const unsigned long long total_chunks = (unsigned long long)G.chunks_per_frame * A.nframes;
-    long long grid = std::max(1ll, std::min<long long>((long long)num_sms * per_sm, (long long)((total_chunks + 7) / 8)));
-    timing_begin(T_GATHER, st);
-    launch_scan_gather(G, (int)grid, st);
-    timing_end(T_GATHER, st);
-    g_launches++;
-    if ((rc = check_launch("gather scan"))) return rc;
+  // ---- gather-v2: the Q1 stragglers of the tile warps + the 16x16-window blocks of the untiled scales
+  {
+    TiledArgs G = T;
+    G.ks = round_ks(g_opt.gather_ks.load());
+    G.consume_q1 = tiled_ran ? 1 : 0;
+    G.tile_warps = 0;
+    if (!blocks_done && first_untiled < A.nscales) {
+      if ((rc = upload_block_prefix(w, first_untiled, A.nscales, st, &G.gather_blocks_per_frame))) return rc;
+      G.gather_scale_lo = first_untiled;
+    }
+    if (G.consume_q1 || G.gather_blocks_per_frame > 0) {
+      min_handover_tree = std::min(min_handover_tree, G.ks);
+      const size_t smem = ((384 + (size_t)G.ks * 516 + 127) & ~(size_t)127);
+      int per_sm = (int)g_opt.gather_ctas_per_sm.load();
+      const int occ = gather2_ctas_per_sm(smem);
+      if (per_sm <= 0 || per_sm > occ) per_sm = occ;
+      timing_begin(T_GATHER, st);
+      launch_scan_gather2(G, num_sms * per_sm, smem, st);
+      timing_end(T_GATHER, st);
+      g_launches++;
+      if ((rc = check_launch("gather-v2 scan"))) return rc;
+    }
   }
 
-  // ---- resume kernel for the deep queue
-  if (A.deep != nullptr) {
-    ScanArgs R = A;
-    R.scale_lo = 0; R.scale_hi = A.nscales;
-    R.chunk_counter = d_work + 2;
-    R.chunks_per_frame = 0;
-    const int per_sm = gather_max_ctas_per_sm(6, false);
+  // ---- deep kernel: Q2, one warp per window, 32 trees per step
+  {
+    // smallest tree index an item in Q2 can carry: the resident prefix of whichever kernel handed it over
+    int kd = min_handover_tree & ~3;   // 16-byte aligned start of the copied table tail
+    const size_t tail_bytes = (size_t)(A.tab.ntrees - kd) * 516 + 16;
     timing_begin(T_DEEP, st);
-    launch_scan_resume(R, num_sms * std::min(per_sm, 4), st);
+    if (g_opt.deep_smem.load() && tail_bytes + 128 <= kSmemPerCta) launch_deep_smem(A, d_work + 3, (const uint8_t*)c->tiled_tab.p, kd, num_sms, st);
+    else launch_deep(A, d_work + 3, num_sms * 8, st);
     timing_end(T_DEEP, st);
     g_launches++;
-    if ((rc = check_launch("resume scan"))) return rc;
+    if ((rc = check_launch("deep scan"))) return rc;
   }
   return PIGO_OK;
 }

@@ -23,21 +23,6 @@
 
 namespace pigo {
 
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ float lds_f32(uint32_t a) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-  return v;
-}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -67,64 +52,265 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
+constexpr uint32_t kCascOff = 384;  // mbarriers live in the first 384 bytes of shared memory
 constexpr int kTreeRec = 516;  // bytes per tree record in the tiled table: 256 codes + 256 leaves + 4 threshold (depth 6)
-
-// Walks tree record `tb` (shared-memory byte address) for the window whose centre pixel is at shared address pb.
-__device__ __forceinline__ int walk_smem(uint32_t tb, uint32_t pb, int s, int pitch) {
-  int idx = 1;
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const int cw = (int)lds_u32(tb + 4 * idx);
-    // ((r*256 + code*s) >> 8) == r + ((code*s) >> 8)  (core/pigo.go:126-127)
-    const int o1 = (((int)(int8_t)(cw) * s) >> 8) * pitch + (((int)(int8_t)(cw >> 8) * s) >> 8);
-    const int o2 = (((int)(int8_t)(cw >> 16) * s) >> 8) * pitch + (((cw >> 24) * s) >> 8);
-    const uint32_t p1 = lds_u8(pb + o1), p2 = lds_u8(pb + o2);
-    idx = 2 * idx + (p1 <= p2 ? 1 : 0);  // core/pigo.go:129-135
-  }
-  return idx;
-}
-// Same walk with the node codes read from the reference-layout table in global memory (trees >= KS, queue full).
-__device__ __forceinline__ int walk_smem_pixels_global_codes(const int8_t* __restrict__ tc, uint32_t pb, int s, int pitch) {
-  int idx = 1;
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const int cw = __ldg(reinterpret_cast<const int*>(tc) + idx);
-    const int o1 = (((int)(int8_t)(cw) * s) >> 8) * pitch + (((int)(int8_t)(cw >> 8) * s) >> 8);
-    const int o2 = (((int)(int8_t)(cw >> 16) * s) >> 8) * pitch + (((cw >> 24) * s) >> 8);
-    const uint32_t p1 = lds_u8(pb + o1), p2 = lds_u8(pb + o2);
-    idx = 2 * idx + (p1 <= p2 ? 1 : 0);
-  }
-  return idx;
-}
 
 __device__ __forceinline__ int ceil_div_pos(int num, int den) { return num <= 0 ? 0 : (num + den - 1) / den; }
 
-template <int NI, bool ALIGNED>
-__global__ void __launch_bounds__(kTiledMaxThreads, 1) scan_tiled_kernel(const TiledArgs A) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
-  const uint32_t bar = smem_base;                 // 8-byte mbarrier at offset 0
-  const uint32_t casc = smem_base + 16;           // cascade prefix records
-  const uint32_t casc_bytes = (uint32_t)A.ks * kTreeRec;
-  const uint32_t tiles0 = (16 + casc_bytes + 127) & ~127u;
-  const uint32_t my_tile = smem_base + tiles0 + (uint32_t)warp * A.tile_bytes;
+// sign-extended byte k of a packed code word: one PRMT (selector nibble with bit 3 set replicates the sign)
+// (prmt.b32 default mode; __byte_perm() documents only 3 selector bits, so the PTX instruction is spelled out)
+__device__ __forceinline__ int sx0(int w) { int r; asm("prmt.b32 %0, %1, 0, 0x8880;" : "=r"(r) : "r"(w)); return r; }
+__device__ __forceinline__ int sx1(int w) { int r; asm("prmt.b32 %0, %1, 0, 0x9991;" : "=r"(r) : "r"(w)); return r; }
+__device__ __forceinline__ int sx2(int w) { int r; asm("prmt.b32 %0, %1, 0, 0xAAA2;" : "=r"(r) : "r"(w)); return r; }
+__device__ __forceinline__ int sx3(int w) { return w >> 24; }
 
-  // ---- stage the cascade prefix with the TMA bulk engine (one elected thread issues, all threads wait)
+// ---- gather role ---------------------------------------------------------------------------------------------
+// Warps >= tile_warps of the fused kernel: the scales too large for a shared-memory tile.  Same lane-refill loop
+// as scan_gather_kernel, but (a) node codes / leaves / thresholds of the first KS trees come from the shared-memory
+// cascade prefix, and (b) work is handed out as 2-D blocks of 16x16 windows of one scale, so that the pixels a
+// CTA touches stay L1-resident instead of streaming whole window rows through L2.
+template <int NG>
+__device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* smem, uint32_t casc, uint32_t casc_end) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const ScanArgs& S = A.scan;
+  const FaceTables T = S.tab;
+  const unsigned long long total_blocks = (unsigned long long)A.gather_blocks_per_frame * S.nframes;
+  const uint32_t q1n = A.consume_q1 ? min(*S.deep_count, S.deep_cap) : 0u;
+  bool q1_more = q1n > 0;
+  bool from_q1 = false;
+  if (total_blocks == 0 && !q1_more) return;
+  const uint32_t tbo_last = casc + (uint32_t)T.ntrees * kTreeRec;   // record offset "one past the last tree"
+
+  // NG independent windows per lane: their dependent LDS -> L2 gather chains overlap (ILP), which is what hides the
+  // ~600-cycle L2 latency when only a few gather warps fit beside the tile warps.
+  bool alive[NG];
+  const uint8_t* pc[NG];
+  int sv[NG], fr[NG];
+  uint32_t tbo[NG], wid[NG];
+  float acc[NG];
+#pragma unroll
+  for (int u = 0; u < NG; ++u) { alive[u] = false; pc[u] = S.frames; sv[u] = 0; fr[u] = 0; tbo[u] = casc; wid[u] = 0; acc[u] = 0.f; }
+  // per-warp block cursor (uniform)
+  uint32_t cur = 0, end = 0;
+  int b_s = 0, b_step = 0, b_r0 = 0, b_c0 = 0, b_w = 1, b_ncols = 0, cframe = 0;
+  uint32_t b_wid0 = 0;
+  bool more = true;
+
+  for (;;) {
+    unsigned live_any = 0;
+#pragma unroll
+    for (int u = 0; u < NG; ++u) {
+      unsigned need = __ballot_sync(FULL, !alive[u]);
+      while (need && more) {
+        if (cur == end) {
+          unsigned long long g = 0;
+          if (q1_more) {                       // stragglers first: 32 queue items per grab
+            if (lane == 0) g = atomicAdd(A.q1_counter, 1ull);
+            g = __shfl_sync(FULL, g, 0);
+            if (g * 32ull < q1n) {
+              from_q1 = true;
+              cur = (uint32_t)g * 32u; end = min(cur + 32u, q1n);
+              continue;
+            }
+            q1_more = false;
+          }
+          from_q1 = false;
+          if (total_blocks == 0) { more = false; break; }
+          if (lane == 0) g = atomicAdd(A.gather_counter, 1ull);
+          g = __shfl_sync(FULL, g, 0);
+          if (g >= total_blocks) { more = false; break; }
+          cframe = (int)(g / A.gather_blocks_per_frame);
+          const uint32_t bidx = (uint32_t)(g % A.gather_blocks_per_frame);
+          int lo = A.gather_scale_lo, hi = S.nscales - 1;   // ladder entry whose block range contains bidx
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (__ldg(&S.plan[mid].pad) <= bidx) lo = mid; else hi = mid - 1;
+          }
+          const ScaleEntry e = S.plan[lo];
+          const uint32_t local = bidx - e.pad;
+          const uint32_t nbx = (uint32_t)(e.ncols + 15) >> 4;
+          const uint32_t by = local / nbx, bx = local - by * nbx;
+          b_w = min(16, e.ncols - (int)bx * 16);
+          const int b_h = min(16, e.nrows - (int)by * 16);
+          b_s = e.s; b_step = e.step; b_ncols = e.ncols;
+          b_r0 = e.off + (int)by * 16 * e.step;
+          b_c0 = e.off + (int)bx * 16 * e.step;
+          b_wid0 = e.wbase + by * 16u * (uint32_t)e.ncols + bx * 16u;
+          cur = 0; end = (uint32_t)(b_w * b_h);
+          continue;
+        }
+        const uint32_t avail = end - cur;
+        const uint32_t rank = __popc(need & lanemask_lt());
+        if (!alive[u] && rank < avail) {
+          const uint32_t k = cur + rank;
+          if (from_q1) {
+            const DeepItem it = S.deep[k];
+            const int si = find_scale(S.plan, S.nscales, it.wid);
+            const ScaleEntry e = S.plan[si];
+            const uint32_t local = it.wid - e.wbase;
+            const uint32_t ri = local / (uint32_t)e.ncols, ci = local - ri * (uint32_t)e.ncols;
+            wid[u] = it.wid; sv[u] = e.s; fr[u] = it.frame;
+            pc[u] = S.frames + (size_t)it.frame * S.frame_stride + (size_t)(e.off + (int)ri * e.step) * S.dim + (e.off + (int)ci * e.step);
+            tbo[u] = casc + (uint32_t)it.tree * kTreeRec; acc[u] = it.acc;
+          } else {
+            const uint32_t ly = b_w == 16 ? (k >> 4) : k / (uint32_t)b_w;
+            const uint32_t lx = k - ly * (uint32_t)b_w;
+            const int r = b_r0 + (int)ly * b_step, c = b_c0 + (int)lx * b_step;
+            wid[u] = b_wid0 + ly * (uint32_t)b_ncols + lx;
+            sv[u] = b_s; fr[u] = cframe;
+            pc[u] = S.frames + (size_t)cframe * S.frame_stride + (size_t)r * S.dim + c;
+            tbo[u] = casc; acc[u] = 0.f;
+          }
+          alive[u] = true;
+        }
+        cur += min((uint32_t)__popc(need), avail);
+        need = __ballot_sync(FULL, !alive[u]);
+      }
+      live_any |= ~need;
+    }
+    if (!live_any) break;
+
+    // ---- one tree per live window; dead slots redo tree 0 at their last pixel with s = 0 (harmless)
+    bool beyond = false;
+#pragma unroll
+    for (int u = 0; u < NG; ++u) {
+      if (!alive[u]) { tbo[u] = casc; sv[u] = 0; }
+      beyond |= tbo[u] >= casc_end;
+    }
+    int idx[NG];
+    float pred[NG], thr[NG];
+    if (!__any_sync(FULL, beyond)) {
+#pragma unroll
+      for (int u = 0; u < NG; ++u) idx[u] = 1;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        int cw[NG];
+#pragma unroll
+        for (int u = 0; u < NG; ++u) cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4 * idx[u]);
+        unsigned p1[NG], p2[NG];
+#pragma unroll
+        for (int u = 0; u < NG; ++u) {
+          const int s = sv[u];
+          const int o1 = ((sx0(cw[u]) * s) >> 8) * S.dim + ((sx1(cw[u]) * s) >> 8);
+          const int o2 = ((sx2(cw[u]) * s) >> 8) * S.dim + ((sx3(cw[u]) * s) >> 8);
+          p1[u] = __ldg(pc[u] + o1);
+          p2[u] = __ldg(pc[u] + o2);
+        }
+#pragma unroll
+        for (int u = 0; u < NG; ++u) idx[u] = 2 * idx[u] + (p1[u] <= p2[u] ? 1 : 0);
+      }
+#pragma unroll
+      for (int u = 0; u < NG; ++u) {
+        pred[u] = *reinterpret_cast<const float*>(smem + tbo[u] + 4 * idx[u]);
+        thr[u] = *reinterpret_cast<const float*>(smem + tbo[u] + 512);
+      }
+    } else {
+      // some window is past the resident prefix and could not be handed over (Q2 full, or a Q1 item already beyond
+      // the prefix): per-slot walk with a table-source switch
+#pragma unroll
+      for (int u = 0; u < NG; ++u) {
+        const bool res = tbo[u] < casc_end;
+        const int tv = (int)((tbo[u] - casc) / kTreeRec);
+        const int* tc = reinterpret_cast<const int*>(T.codes + (size_t)tv * 256);
+        int ix = 1;
+        const int s = sv[u];
+        for (int j = 0; j < 6; ++j) {
+          const int cw = res ? *reinterpret_cast<const int*>(smem + tbo[u] + 4 * ix) : __ldg(tc + ix);
+          const int o1 = ((sx0(cw) * s) >> 8) * S.dim + ((sx1(cw) * s) >> 8);
+          const int o2 = ((sx2(cw) * s) >> 8) * S.dim + ((sx3(cw) * s) >> 8);
+          const unsigned q1 = __ldg(pc[u] + o1), q2 = __ldg(pc[u] + o2);
+          ix = 2 * ix + (q1 <= q2 ? 1 : 0);
+        }
+        idx[u] = ix;
+        pred[u] = res ? *reinterpret_cast<const float*>(smem + tbo[u] + 4 * ix) : __ldg(T.preds + (size_t)tv * 64 + ix - 64);
+        thr[u] = res ? *reinterpret_cast<const float*>(smem + tbo[u] + 512) : __ldg(T.thresh + tv);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NG; ++u) {
+      if (alive[u]) {
+        acc[u] += pred[u];                               // core/pigo.go:137
+        tbo[u] += kTreeRec;
+        if (acc[u] <= thr[u]) {                          // :139-141
+          alive[u] = false;
+        } else if (tbo[u] == tbo_last) {
+          const float q = acc[u] - thr[u];               // :144
+          if (q > 0.0f) {                                // :246
+            const int pos = atomicAdd(S.raw_count + fr[u], 1);
+            if (pos < S.cap) S.raw[(size_t)fr[u] * S.cap + pos] = RawDet{wid[u], q};
+          }
+          alive[u] = false;
+        } else if (tbo[u] >= casc_end && S.longq != nullptr) {
+          // survived the resident trees: hand over to the deep (32-trees-per-step) kernel; if its queue is full
+          // the window simply continues here on the global tables
+          const unsigned pos = atomicAdd(S.long_count, 1u);
+          if (pos < S.long_cap) {
+            S.longq[pos] = DeepItem{wid[u], fr[u], (int)((tbo[u] - casc) / kTreeRec), acc[u]};
+            alive[u] = false;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Stages the first KS tree records into shared memory with the TMA bulk engine; returns after all threads see them.
+__device__ __forceinline__ void stage_cascade(const TiledArgs& A, uint32_t smem_base, uint32_t casc, uint32_t casc_bytes) {
+  const uint32_t bar = smem_base;
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(bar, casc_bytes);
     for (uint32_t off = 0; off < casc_bytes; off += 32768) {
       const uint32_t n = min(32768u, casc_bytes - off);
-      tma_bulk_g2s(casc + off, A.tab_tiled + off, n, bar);
+      tma_bulk_g2s(smem_base + casc + off, A.tab_tiled + off, n, bar);
     }
   }
   __syncthreads();
   mbar_wait(bar, 0);
+}
+
+// gather-v2: every warp plays the gather role (untiled scales in 16x16-window blocks + the Q1 stragglers), with the
+// cascade prefix in shared memory.  256 threads, several CTAs per SM.
+__global__ void __launch_bounds__(256, 4) scan_gather2_kernel(const TiledArgs A) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t casc = kCascOff;
+  const uint32_t casc_bytes = (uint32_t)A.ks * kTreeRec;
+  stage_cascade(A, smem_base, casc, (casc_bytes + 15u) & ~15u);
+  if (A.gather_ni >= 3) gather_role<3>(A, smem, casc, casc + casc_bytes);
+  else if (A.gather_ni == 2) gather_role<2>(A, smem, casc, casc + casc_bytes);
+  else gather_role<1>(A, smem, casc, casc + casc_bytes);
+}
+
+template <int NI, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t wbar = smem_base + 16 + 8 * warp; // per-warp mbarrier: tile arrival
+  const uint32_t casc = kCascOff;                 // byte offset of the cascade prefix records inside smem[]
+  const uint32_t casc_bytes = (uint32_t)A.ks * kTreeRec;
+  const uint32_t casc_end = casc + casc_bytes;    // record offset of tree KS (first tree NOT resident)
+  const uint32_t tiles0 = (kCascOff + ((casc_bytes + 15u) & ~15u) + 127) & ~127u;
+  const uint32_t my_tile = tiles0 + (uint32_t)warp * A.tile_bytes;
+
+  // ---- stage the cascade prefix with the TMA bulk engine (one elected thread issues, all threads wait)
+  if (lane == 0 && warp < A.tile_warps) mbar_init(wbar, 1);
+  stage_cascade(A, smem_base, casc, (casc_bytes + 15u) & ~15u);
 
   const ScanArgs& S = A.scan;
+  if (warp >= A.tile_warps) {   // warp-specialised: the remaining warps scan the large scales by global-memory gathers
+    if (A.gather_ni >= 2) gather_role<2>(A, smem, casc, casc_end);
+    else gather_role<1>(A, smem, casc, casc_end);
+    return;
+  }
+  uint32_t tile_phase = 0;
+  const bool all_resident = A.ks >= S.tab.ntrees;  // then reaching casc_end means "survived the whole cascade"
+  bool overflow_mode = false;                      // warp-uniform: a hand-over to the deep queue failed (queue full)
 
   for (;;) {
     // ---- next tile for this warp
@@ -158,134 +344,225 @@ __global__ void __launch_bounds__(kTiledMaxThreads, 1) scan_tiled_kernel(const T
 
     // ---- fill the tile: rows [gy0, gy0+rows_t) x bytes [gx0, gx0+pitch) clipped to the frame
     __syncwarp();
-    if (ALIGNED) {
-      const int cpr = pitch >> 4;
-      const int nchunks = B.rows_t * cpr;
-      for (int q = lane; q < nchunks; q += 32) {
-        const int row = q / cpr, cxk = q - row * cpr;
-        const int y = gy0 + row, x = gx0 + 16 * cxk;
-        if (y >= 0 && y < S.rows && x >= 0 && x < S.dim) cp_async16(my_tile + row * pitch + 16 * cxk, fb + (size_t)y * S.dim + x);
-      }
-      cp_async_wait_all();
+    if (A.aligned) {
+      // one TMA bulk copy per tile row (16-byte aligned, clipped to the frame), completion on the warp's mbarrier
+      const int y_lo = max(gy0, 0), y_hi = min(gy0 + B.rows_t, S.rows);
+      const int x_lo = max(gx0, 0), x_hi = min(gx0 + pitch, S.dim);
+      const uint32_t row_bytes = (uint32_t)(x_hi - x_lo);
+      if (lane == 0) mbar_expect_tx(wbar, row_bytes * (uint32_t)(y_hi - y_lo));
+      __syncwarp();
+      for (int y = y_lo + lane; y < y_hi; y += 32)
+        tma_bulk_g2s(smem_base + my_tile + (uint32_t)((y - gy0) * pitch + (x_lo - gx0)), fb + (size_t)y * S.dim + x_lo, row_bytes, wbar);
+      mbar_wait(wbar, tile_phase);
+      tile_phase ^= 1u;
     } else {
       const int nbytes = B.rows_t * pitch;
       for (int q = lane; q < nbytes; q += 32) {
         const int row = q / pitch, xx = q - row * pitch;
         const int y = gy0 + row, x = gx0 + xx;
-        if (y >= 0 && y < S.rows && x >= 0 && x < S.dim) {
-          const uint32_t v = __ldg(fb + (size_t)y * S.dim + x);
-          asm volatile("st.shared.u8 [%0], %1;" ::"r"(my_tile + q), "r"(v) : "memory");
-        }
+        if (y >= 0 && y < S.rows && x >= 0 && x < S.dim) smem[my_tile + q] = __ldg(fb + (size_t)y * S.dim + x);
       }
     }
     __syncwarp();
 
     // uniform cursor over the tile's window list (scale-major)
     int cur_si = -1, cur_k = 0, cur_n = 0;
-    int u_s = 0, u_step = 0, u_off = 0, u_i0 = 0, u_j0 = 0, u_nj = 1, u_ncols = 0;
-    uint32_t u_wbase = 0, u_magic = 0;
+    int u_s = 0, u_step = 0, u_nj = 1, u_ncols = 0, u_br = 0, u_bc = 0;
+    uint32_t u_wid0 = 0, u_magic = 0;
     bool exhausted = false;
 
     bool alive[NI];
-    uint32_t pb[NI], tb[NI], wid[NI];
-    int sv[NI], tv[NI];
+    uint32_t pb[NI], tbo[NI], wid[NI];
+    int sv[NI];
     float acc[NI];
 #pragma unroll
-    for (int u = 0; u < NI; ++u) { alive[u] = false; pb[u] = my_tile; tb[u] = casc; wid[u] = 0; sv[u] = 0; tv[u] = 0; acc[u] = 0.f; }
+    for (int u = 0; u < NI; ++u) { alive[u] = false; pb[u] = my_tile; tbo[u] = casc; wid[u] = 0; sv[u] = 0; acc[u] = 0.f; }
 
     for (;;) {
-      // ---- refill dead slots from the tile's window list
-      bool any_alive = false;
+      // ================= refill dead slots from the tile's window list ==========================================
+      // Fast path (straight-line, one uniform branch): all dead slots of all NI groups take consecutive windows
+      // of the current scale.  The serial path below handles scale changes, the end of the tile and its tail.
+      unsigned need[NI];
+      int total = 0;
 #pragma unroll
-      for (int u = 0; u < NI; ++u) {
-        unsigned need = __ballot_sync(FULL, !alive[u]);
-        while (need && !exhausted) {
-          if (cur_k == cur_n) {
-            // advance to the next scale of the band that has windows in this tile
-            int nsi = cur_si + 1;
-            int n = 0;
-            while (nsi < B.nscales && (n = __shfl_sync(FULL, sc_n, nsi)) == 0) ++nsi;
-            if (nsi >= B.nscales) { exhausted = true; break; }
-            cur_si = nsi; cur_k = 0; cur_n = n;
-            u_s = __shfl_sync(FULL, e.s, nsi); u_step = __shfl_sync(FULL, e.step, nsi); u_off = __shfl_sync(FULL, e.off, nsi);
-            u_i0 = __shfl_sync(FULL, sc_i0, nsi); u_j0 = __shfl_sync(FULL, sc_j0, nsi); u_nj = __shfl_sync(FULL, sc_nj, nsi);
-            u_ncols = __shfl_sync(FULL, e.ncols, nsi); u_wbase = __shfl_sync(FULL, e.wbase, nsi);
-            u_magic = (uint32_t)((0x100000000ull + (unsigned)u_nj - 1) / (unsigned)u_nj);  // ceil(2^32 / nj)
-            continue;
+      for (int u = 0; u < NI; ++u) { need[u] = __ballot_sync(FULL, !alive[u]); total += __popc(need[u]); }
+      if (total != 0) {
+        if (!exhausted && cur_k + total <= cur_n) {
+          int base = cur_k;
+#pragma unroll
+          for (int u = 0; u < NI; ++u) {
+            if (!alive[u]) {
+              const uint32_t k = (uint32_t)(base + __popc(need[u] & lanemask_lt()));
+              const uint32_t i = u_nj > 1 ? __umulhi(k, u_magic) : k;   // k / nj, exact for k*nj < 2^32
+              const uint32_t j = k - i * (uint32_t)u_nj;
+              pb[u] = my_tile + (uint32_t)((u_br + (int)i * u_step) * pitch + u_bc + (int)j * u_step);
+              wid[u] = u_wid0 + i * (uint32_t)u_ncols + j;
+              sv[u] = u_s; tbo[u] = casc; acc[u] = 0.f;
+              alive[u] = true;
+            }
+            base += __popc(need[u]);
           }
-          const int avail = cur_n - cur_k;
-          const int rank = __popc(need & lanemask_lt());
-          if (!alive[u] && rank < avail) {
-            const uint32_t k = (uint32_t)(cur_k + rank);
-            const uint32_t i = u_nj == 1 ? k : __umulhi(k, u_magic);   // k / nj, exact for k*nj < 2^32
-            const uint32_t j = k - i * (uint32_t)u_nj;
-            const int gi = u_i0 + (int)i, gj = u_j0 + (int)j;
-            const int r = u_off + gi * u_step, c = u_off + gj * u_step;
-            pb[u] = my_tile + (uint32_t)((r - gy0) * pitch + (c - gx0));
-            wid[u] = u_wbase + (uint32_t)gi * (uint32_t)u_ncols + (uint32_t)gj;
-            sv[u] = u_s; tv[u] = 0; tb[u] = casc; acc[u] = 0.f;
-            alive[u] = true;
+          cur_k += total;
+        } else {
+          unsigned live_any = 0;
+#pragma unroll
+          for (int u = 0; u < NI; ++u) {
+            unsigned nd = need[u];
+            while (nd && !exhausted) {
+              if (cur_k == cur_n) {
+                // advance to the next scale of the band that has windows in this tile
+                int nsi = cur_si + 1;
+                int n = 0;
+                while (nsi < B.nscales && (n = __shfl_sync(FULL, sc_n, nsi)) == 0) ++nsi;
+                if (nsi >= B.nscales) { exhausted = true; break; }
+                cur_si = nsi; cur_k = 0; cur_n = n;
+                u_s = __shfl_sync(FULL, e.s, nsi); u_step = __shfl_sync(FULL, e.step, nsi);
+                const int off = __shfl_sync(FULL, e.off, nsi), i0 = __shfl_sync(FULL, sc_i0, nsi), j0 = __shfl_sync(FULL, sc_j0, nsi);
+                u_nj = __shfl_sync(FULL, sc_nj, nsi); u_ncols = __shfl_sync(FULL, e.ncols, nsi);
+                u_br = off + i0 * u_step - gy0;   // tile row of the sub-grid's first window centre
+                u_bc = off + j0 * u_step - gx0;
+                u_wid0 = __shfl_sync(FULL, e.wbase, nsi) + (uint32_t)i0 * (uint32_t)u_ncols + (uint32_t)j0;
+                u_magic = u_nj > 1 ? (uint32_t)((0x100000000ull + (unsigned)u_nj - 1) / (unsigned)u_nj) : 0u;  // ceil(2^32/nj)
+                continue;
+              }
+              const int avail = cur_n - cur_k;
+              const int rank = __popc(nd & lanemask_lt());
+              if (!alive[u] && rank < avail) {
+                const uint32_t k = (uint32_t)(cur_k + rank);
+                const uint32_t i = u_nj > 1 ? __umulhi(k, u_magic) : k;
+                const uint32_t j = k - i * (uint32_t)u_nj;
+                pb[u] = my_tile + (uint32_t)((u_br + (int)i * u_step) * pitch + u_bc + (int)j * u_step);
+                wid[u] = u_wid0 + i * (uint32_t)u_ncols + j;
+                sv[u] = u_s; tbo[u] = casc; acc[u] = 0.f;
+                alive[u] = true;
+              }
+              cur_k += min(__popc(nd), avail);
+              nd = __ballot_sync(FULL, !alive[u]);
+            }
+            // ---- tail policy: once the tile is drained, a thin slot group is handed to the deep queue
+            unsigned live = ~nd;
+            if (exhausted && live != 0u && __popc(live) < A.tail_min && !overflow_mode) {
+              unsigned qbase = 0;
+              if (lane == 0) qbase = atomicAdd(S.deep_count, (unsigned)__popc(live));
+              qbase = __shfl_sync(FULL, qbase, 0);
+              const unsigned pos = qbase + __popc(live & lanemask_lt());
+              if (alive[u] && pos < S.deep_cap) {
+                S.deep[pos] = DeepItem{wid[u], frame, (int)((tbo[u] - casc) / kTreeRec), acc[u]};
+                alive[u] = false;
+              }
+              live = __ballot_sync(FULL, alive[u]);
+              if (live) overflow_mode = true;   // queue full: finish these items here
+            }
+            live_any |= live;
           }
-          cur_k += min(__popc(need), avail);
-          need = __ballot_sync(FULL, !alive[u]);
+          if (!live_any) break;
+          // dead slots walk a harmless dummy (tree 0 at a valid pixel with s = 0)
+#pragma unroll
+          for (int u = 0; u < NI; ++u)
+            if (!alive[u]) { tbo[u] = casc; sv[u] = 0; }
         }
-        // ---- tail policy: once the tile is drained, a thin slot group is handed to the deep queue
-        const unsigned live = ~need;
-        if (exhausted && live != 0u && __popc(live) < A.tail_min) {
-          unsigned base = 0;
-          if (lane == 0) base = atomicAdd(S.deep_count, (unsigned)__popc(live));
-          base = __shfl_sync(FULL, base, 0);
-          const unsigned pos = base + __popc(live & lanemask_lt());
-          if (alive[u] && pos < S.deep_cap) {
-            S.deep[pos] = DeepItem{wid[u], frame, tv[u], acc[u]};
-            alive[u] = false;
-          }
-        }
-        any_alive |= __any_sync(FULL, alive[u]);
       }
-      if (!any_alive) break;
 
-      // ---- one tree per live item (dead slots walk a harmless dummy: tree 0 at the tile origin with s = 0)
-      int idx[NI];
+      // ================= one tree per live item =================================================================
+      if (!overflow_mode) {
+        int idx[NI];
 #pragma unroll
-      for (int u = 0; u < NI; ++u) {
-        if (!alive[u]) { tv[u] = 0; tb[u] = casc; sv[u] = 0; }
-        if (tv[u] < A.ks) {
-          idx[u] = walk_smem(tb[u], pb[u], sv[u], pitch);
-        } else {
-          idx[u] = walk_smem_pixels_global_codes(S.tab.codes + (size_t)tv[u] * 256, pb[u], sv[u], pitch);
-        }
-      }
+        for (int u = 0; u < NI; ++u) idx[u] = 1;
 #pragma unroll
-      for (int u = 0; u < NI; ++u) {
-        float pred, thr;
-        if (tv[u] < A.ks) {
-          pred = lds_f32(tb[u] + 256 + 4 * (idx[u] - 64));
-          thr = lds_f32(tb[u] + 512);
-        } else {
-          pred = __ldg(S.tab.preds + (size_t)tv[u] * 64 + idx[u] - 64);
-          thr = __ldg(S.tab.thresh + tv[u]);
+        for (int j = 0; j < 6; ++j) {
+          int cw[NI];
+#pragma unroll
+          for (int u = 0; u < NI; ++u) cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4 * idx[u]);
+          uint32_t p1[NI], p2[NI];
+#pragma unroll
+          for (int u = 0; u < NI; ++u) {
+            // ((r*256 + code*s) >> 8) == r + ((code*s) >> 8)  (core/pigo.go:126-127)
+            const int s = sv[u];
+            const int o1 = ((sx0(cw[u]) * s) >> 8) * pitch + ((sx1(cw[u]) * s) >> 8);
+            const int o2 = ((sx2(cw[u]) * s) >> 8) * pitch + ((sx3(cw[u]) * s) >> 8);
+            p1[u] = smem[pb[u] + o1];
+            p2[u] = smem[pb[u] + o2];
+          }
+#pragma unroll
+          for (int u = 0; u < NI; ++u) idx[u] = 2 * idx[u] + (p1[u] <= p2[u] ? 1 : 0);   // core/pigo.go:129-135
         }
-        if (alive[u]) {
+        bool hit = false;
+        float thr_last[NI];
+#pragma unroll
+        for (int u = 0; u < NI; ++u) {
+          const float pred = *reinterpret_cast<const float*>(smem + tbo[u] + 4 * idx[u]);  // leaves at words 64..127
+          const float thr = *reinterpret_cast<const float*>(smem + tbo[u] + 512);
+          thr_last[u] = thr;
           acc[u] += pred;                                   // core/pigo.go:137 (float32, tree order)
-          if (acc[u] <= thr) {                              // :139-141
-            alive[u] = false;
-          } else {
-            ++tv[u];
-            tb[u] += kTreeRec;
-            if (tv[u] == S.tab.ntrees) {
-              const float q = acc[u] - thr;                 // :144
-              if (q > 0.0f) {                               // :246
+          alive[u] = alive[u] && !(acc[u] <= thr);          // :139-141
+          tbo[u] += kTreeRec;
+          hit |= alive[u] && tbo[u] == casc_end;
+          if (!alive[u]) { tbo[u] = casc; sv[u] = 0; }      // a dead slot walks a harmless dummy until it is refilled
+        }
+        if (__any_sync(FULL, hit)) {                        // some windows passed the last resident tree (rare)
+#pragma unroll
+          for (int u = 0; u < NI; ++u) {
+            const bool at_end = alive[u] && tbo[u] == casc_end;
+            const unsigned mb = __ballot_sync(FULL, at_end);
+            if (!mb) continue;
+            if (all_resident) {
+              if (at_end) {
+                const float q = acc[u] - thr_last[u];       // :144
+                if (q > 0.0f) {                             // :246
+                  const int pos = atomicAdd(S.raw_count + frame, 1);
+                  if (pos < S.cap) S.raw[(size_t)frame * S.cap + pos] = RawDet{wid[u], q};
+                }
+                alive[u] = false;
+              }
+            } else {
+              unsigned qbase = 0;
+              if (lane == 0) qbase = atomicAdd(S.long_count, (unsigned)__popc(mb));
+              qbase = __shfl_sync(FULL, qbase, 0);
+              const unsigned pos = qbase + __popc(mb & lanemask_lt());
+              bool failed = false;
+              if (at_end) {
+                if (pos < S.long_cap) {
+                  S.longq[pos] = DeepItem{wid[u], frame, A.ks, acc[u]};
+                  alive[u] = false;
+                } else {
+                  failed = true;
+                }
+              }
+              if (__any_sync(FULL, failed)) overflow_mode = true;
+            }
+            if (!alive[u]) { tbo[u] = casc; sv[u] = 0; }
+          }
+        }
+      } else {
+        // ---- overflow mode (deep queue full, pathological): correct but slow; cascade rows beyond KS from global
+#pragma unroll
+        for (int u = 0; u < NI; ++u) {
+          const int tv = (int)((tbo[u] - casc) / kTreeRec);
+          const bool res = tbo[u] < casc_end;
+          int idx = 1;
+          for (int j = 0; j < 6; ++j) {
+            const int cw = res ? *reinterpret_cast<const int*>(smem + tbo[u] + 4 * idx)
+                               : __ldg(reinterpret_cast<const int*>(S.tab.codes + (size_t)tv * 256) + idx);
+            const int s = sv[u];
+            const int o1 = ((sx0(cw) * s) >> 8) * pitch + ((sx1(cw) * s) >> 8);
+            const int o2 = ((sx2(cw) * s) >> 8) * pitch + ((sx3(cw) * s) >> 8);
+            const uint32_t p1 = smem[pb[u] + o1], p2 = smem[pb[u] + o2];
+            idx = 2 * idx + (p1 <= p2 ? 1 : 0);
+          }
+          const float pred = res ? *reinterpret_cast<const float*>(smem + tbo[u] + 4 * idx) : __ldg(S.tab.preds + (size_t)tv * 64 + idx - 64);
+          const float thr = res ? *reinterpret_cast<const float*>(smem + tbo[u] + 512) : __ldg(S.tab.thresh + tv);
+          if (alive[u]) {
+            acc[u] += pred;
+            tbo[u] += kTreeRec;
+            if (acc[u] <= thr) {
+              alive[u] = false;
+            } else if (tv + 1 == S.tab.ntrees) {
+              const float q = acc[u] - thr;
+              if (q > 0.0f) {
                 const int pos = atomicAdd(S.raw_count + frame, 1);
                 if (pos < S.cap) S.raw[(size_t)frame * S.cap + pos] = RawDet{wid[u], q};
               }
               alive[u] = false;
-            } else if (tv[u] == A.ks) {
-              const unsigned pos = atomicAdd(S.deep_count, 1u);
-              if (pos < S.deep_cap) {
-                S.deep[pos] = DeepItem{wid[u], frame, tv[u], acc[u]};
-                alive[u] = false;
-              }  // else: queue full -> keep walking with the global cascade rows
             }
           }
         }
@@ -294,23 +571,31 @@ __global__ void __launch_bounds__(kTiledMaxThreads, 1) scan_tiled_kernel(const T
   }
 }
 
-template <int NI>
-static void launch_tiled_ni(const TiledArgs& A, int grid, int threads, size_t smem, bool aligned, cudaStream_t st) {
-  if (aligned) {
-    cudaFuncSetAttribute(scan_tiled_kernel<NI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    scan_tiled_kernel<NI, true><<<grid, threads, smem, st>>>(A);
-  } else {
-    cudaFuncSetAttribute(scan_tiled_kernel<NI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    scan_tiled_kernel<NI, false><<<grid, threads, smem, st>>>(A);
-  }
+template <int NI, int MAXT>
+static void launch_tiled_ni(const TiledArgs& A, int grid, int threads, size_t smem, cudaStream_t st) {
+  cudaFuncSetAttribute(scan_tiled_kernel<NI, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  scan_tiled_kernel<NI, MAXT><<<grid, threads, smem, st>>>(A);
 }
 
-void launch_scan_tiled(const TiledArgs& A, int grid, int threads, size_t smem, int ni, bool aligned, cudaStream_t st) {
+void launch_scan_gather2(const TiledArgs& A, int grid, size_t smem, cudaStream_t st) {
+  cudaFuncSetAttribute(scan_gather2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  scan_gather2_kernel<<<grid, 256, smem, st>>>(A);
+}
+int gather2_ctas_per_sm(size_t smem) {
+  int n = 0;
+  cudaFuncSetAttribute(scan_gather2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan_gather2_kernel, 256, smem) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
+  return n;
+}
+
+int tiled_max_threads(int ni) { return ni == 1 ? 1024 : (ni == 2 ? 768 : 512); }
+
+void launch_scan_tiled(const TiledArgs& A, int grid, int threads, size_t smem, int ni, cudaStream_t st) {
   switch (ni) {
-    case 1: launch_tiled_ni<1>(A, grid, threads, smem, aligned, st); break;
-    case 2: launch_tiled_ni<2>(A, grid, threads, smem, aligned, st); break;
-    case 3: launch_tiled_ni<3>(A, grid, threads, smem, aligned, st); break;
-    default: launch_tiled_ni<4>(A, grid, threads, smem, aligned, st); break;
+    case 1: launch_tiled_ni<1, 1024>(A, grid, threads, smem, st); break;
+    case 2: launch_tiled_ni<2, 768>(A, grid, threads, smem, st); break;
+    case 3: launch_tiled_ni<3, 512>(A, grid, threads, smem, st); break;
+    default: launch_tiled_ni<4, 512>(A, grid, threads, smem, st); break;
   }
 }
 

@@ -248,12 +248,19 @@ VARIANTS = [
     {"scan_mode": 0, "tile_ni": 4, "tile_warps": 12, "tile_ks": 128, "tile_tail_min": 0},  # nothing spills at tails
     {"scan_mode": 0, "tile_ni": 3, "tile_warps": 16, "tile_ks": 468, "tile_band_ratio": 130},
     {"scan_mode": 0, "tile_max_scale": 30, "chunk": 64},
+    {"scan_mode": 0, "gather_warps": 0, "tile_warps": 8, "tile_ni": 2},               # tiles fused kernel + separate gather launch
+    {"scan_mode": 0, "gather_warps": 24, "tile_warps": 8, "tile_ni": 1, "tile_ks": 32},
+    {"scan_mode": 3, "gather_ks": 32, "gather_ni": 1, "sub_batch": 2, "lanes": 2},      # gather-v2 + deep kernel only
+    {"scan_mode": 0, "gather_ni": 3, "sub_batch": 1, "lanes": 3, "deep_smem": 1},
+    {"scan_mode": 3, "gather_ks": 4},                                                   # nearly everything through the deep kernel
+    {"scan_mode": 0, "gather_ks": 468, "tile_ks": 468, "tile_warps": 4, "gather_warps": 0},   # whole cascade resident: no Q2
 ]
 
 
 @pytest.fixture
 def restore_options():
-    keys = ["scan_mode", "tile_ni", "tile_warps", "tile_ks", "tile_tail_min", "tile_band_ratio", "tile_max_scale", "chunk"]
+    keys = ["scan_mode", "tile_ni", "tile_warps", "tile_ks", "tile_tail_min", "tile_band_ratio", "tile_max_scale", "chunk",
+            "gather_warps", "gather_ks", "gather_ni", "sub_batch", "lanes", "deep_smem"]
     saved = {k: pigo_b200.get_option(k) for k in keys}
     yield
     for k, v in saved.items():

@@ -55,8 +55,13 @@ def main():
             e0.record(); run(); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ms = float(np.median(ts))
+        pigo_b200.set_option("timing", 1)
+        run(); torch.cuda.synchronize()
+        kt = {n: pigo_b200.get_option(f"t_{n}_ns") / 1e6 for n in ("tiled", "gather", "deep", "finalize")}
+        pigo_b200.set_option("timing", 0)
         print(f"[{v or 'default'}] frames={args.frames} {args.rows}x{args.cols} shift={args.shift}: {ms:.3f} ms/step  "
-              f"{args.frames * W / ms / 1e6:.1f} Mwin/s  dets={int(d_cnt.sum())} (min {min(ts):.3f} max {max(ts):.3f})", flush=True)
+              f"{args.frames * W / ms / 1e6:.2f} Gwin/s  dets={int(d_cnt.sum())} (min {min(ts):.3f} max {max(ts):.3f}) kernels ms: "
+              + " ".join(f"{k}={v:.3f}" for k, v in kt.items()), flush=True)
 
 
 if __name__ == "__main__":
