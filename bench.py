@@ -235,14 +235,26 @@ def main():
     dom = max(kt.items(), key=lambda kv: kv[1]["total_ms"]) if kt else None
     roofline = None
     if dom:
-        alg_bytes = nf * ROWS * COLS + 16 * ndet + CASCADE_BYTES   # per scan pass over the batch (one step)
+        # One launch of the dominant kernel (the fused scan kernel, "tiled") covers one pipeline group of `sub_batch`
+        # frames: algorithmic bytes per launch = its frames once + its share of the detections + the cascade once.
+        launches_per_step = dom[1]["launches"] / args.steps
+        frames_per_launch = nf / launches_per_step
+        alg_bytes = frames_per_launch * ROWS * COLS + 16 * ndet / launches_per_step + CASCADE_BYTES
         scan_ms = sum(v["total_ms"] for k, v in kt.items() if k != "finalize") / args.steps
-        dom_ms = dom[1]["total_ms"] / args.steps
-        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+        launch_ms = dom[1]["avg_us"] / 1e3
+        achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+            if tr.get("kernel") == dom[0]:
+                traffic = tr["dram_bytes_per_launch"] * frames_per_launch / tr["frames_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": dom[0], "kernel_ms_per_step": dom_ms, "scan_kernels_ms_per_step": scan_ms,
-                    "algorithmic_bytes_per_step": alg_bytes, "peak_source": peak_src, "kernels": kt,
-                    "note": "path is issue/latency bound (2.3 algorithmic B/window); see DESIGN.md"}
+                    "traffic": traffic, "kernel": dom[0], "kernel_launch_ms": launch_ms, "frames_per_launch": frames_per_launch,
+                    "scan_kernels_ms_per_step": scan_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                    "kernels": kt, "note": "path is issue/latency/L2-transaction bound (2.3 algorithmic B/window), not HBM "
+                    "bound; see DESIGN.md"}
 
     # ---- end to end through the host API: pinned H2D of the frames + D2H of counts and detections every step
     out_h = np.zeros((nf, cap), dtype=pigo_b200.DET_DTYPE)

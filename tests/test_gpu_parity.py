@@ -287,3 +287,17 @@ def test_scan_variants_agree_with_oracle(gpu_face, oracle_face, sample_gray, res
     for f in range(3):
         o = oracle_face.run_cascade(frames[f], 720, 1280, 1280, *TEST_PARAMS, 0.0)
         assert cnt[f] == len(o) and dets[f, :cnt[f]].tobytes() == o.tobytes()
+
+
+def test_cpp_mirror_replays_reference_test():
+    """include/pigo_b200.hpp (C++ mirror of the Go API) -> C-ABI -> GPU: core/pigo_test.go:68-84 on the sample image."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "test_mirror")
+    if not os.path.exists(exe):
+        import __graft_entry__
+        __graft_entry__.build()
+    r = subprocess.run([exe, root], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "dets=4 clusters=1" in r.stdout
