@@ -145,6 +145,12 @@ int pigo_get_landmark_point(const pigo_puploc *p, const pigo_point *left_eye, co
                             const uint8_t *pixels, int rows, int cols, int dim, int perturb, int flipv,
                             const float *randoms, uint64_t rng_seed, pigo_point *out);
 
+/* ---- RgbToGrayscale(src image.Image) []uint8, core/grayscale.go:8-23, for *image.NRGBA input (what GetImage returns,
+ * core/image.go:13-33): gray = uint8((0.299 r + 0.587 g + 0.114 b) / 256) in float64 on the 16-bit, alpha-premultiplied
+ * channels color.NRGBA.RGBA() yields.  rgba is [npixels][4] (R,G,B,A), gray is [npixels].  flags: PIGO_FRAMES_DEVICE /
+ * PIGO_OUT_DEVICE say where rgba / gray live.  (the stage just before the hot path.) */
+int pigo_rgba_to_gray(const uint8_t *rgba, size_t npixels, uint8_t *gray, unsigned flags, void *stream);
+
 /* ---- tuning / introspection (not part of the reference surface) ------------------------- */
 /* Selects the scan implementation: 0 = auto (default), 1 = gather kernel only (every window
  * through global-memory gathers), 2 = tiled (shared-memory pixel tiles) + gather for the rest. */

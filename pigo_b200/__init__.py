@@ -41,7 +41,7 @@ ABI_SYMBOLS = [
     "pigo_free_pinned", "pigo_cascade_create", "pigo_cascade_destroy", "pigo_cascade_info", "pigo_scale_ladder",
     "pigo_count_windows", "pigo_run_cascade", "pigo_run_cascade_batch", "pigo_cluster", "pigo_cluster_batch",
     "pigo_puploc_create", "pigo_puploc_destroy", "pigo_puploc_info", "pigo_puploc_run", "pigo_get_landmark_point",
-    "pigo_set_option", "pigo_get_option",
+    "pigo_set_option", "pigo_get_option", "pigo_rgba_to_gray",
 ]
 
 
@@ -85,6 +85,7 @@ def lib() -> C.CDLL:
         L.pigo_puploc_info.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.pigo_puploc_run.argtypes = [vp, vp, i, vp, u64, vp, i, i, i, d, vp, vp, C.c_uint, vp]
         L.pigo_get_landmark_point.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp, u64, vp]
+        L.pigo_rgba_to_gray.argtypes = [vp, sz, vp, C.c_uint, vp]
         L.pigo_set_option.argtypes = [C.c_char_p, C.c_int64]
         L.pigo_get_option.argtypes = [C.c_char_p]
         L.pigo_get_option.restype = C.c_int64
@@ -379,6 +380,17 @@ class FlpCascade:
 
     def GetLandmarkPoint(self, *a, **k):
         return self.PuplocCascade.GetLandmarkPoint(*a, **k)
+
+
+def RgbToGrayscale(rgba: np.ndarray) -> np.ndarray:
+    """pigo.RgbToGrayscale, core/grayscale.go:8-23, for an NRGBA pixel array [..., 4] (R, G, B, A); returns uint8 [...]."""
+    a = np.ascontiguousarray(rgba, dtype=np.uint8)
+    if a.shape[-1] != 4:
+        raise ValueError("expected [..., 4] NRGBA pixels")
+    n = a.size // 4
+    out = np.zeros(a.shape[:-1], dtype=np.uint8)
+    _check(lib().pigo_rgba_to_gray(a.ctypes.data if n else None, n, out.ctypes.data if n else None, MEM_HOST, None))
+    return out
 
 
 def load_cascade(name: str = "facefinder") -> bytes:

@@ -30,7 +30,7 @@ struct TimingSlot {
 };
 static TimingSlot g_tslot[T_NSLOTS];
 static std::mutex g_tmu;
-static const char* kSlotNames[T_NSLOTS] = {"tiled", "gather", "deep", "finalize", "cluster", "puploc"};
+static const char* kSlotNames[T_NSLOTS] = {"tiled", "gather", "deep", "finalize", "cluster", "puploc", "gray"};
 
 void timing_reset() {
   std::lock_guard<std::mutex> g(g_tmu);
@@ -335,9 +335,14 @@ int pigo_run_cascade_batch(const pigo_cascade* cc, const uint8_t* frames, int nf
   int32_t* d_rawcount = (int32_t*)w->counters.p;
   unsigned long long* d_work = (unsigned long long*)((char*)w->counters.p + work_off);
 
-  if (lanes > 1) {
-    CUDA_TRY(cudaEventRecord(w->ev_fork, st));
-    for (int l = 0; l < lanes; ++l) CUDA_TRY(cudaStreamWaitEvent(w->lane_stream[l], w->ev_fork, 0));
+  if (lanes > 1 || !frames_dev) {
+    CUDA_TRY(cudaEventRecord(w->ev_fork, st));   // everything queued on `st` so far (previous results, memset) comes first
+    for (int l = 0; l < lanes && lanes > 1; ++l) CUDA_TRY(cudaStreamWaitEvent(w->lane_stream[l], w->ev_fork, 0));
+    if (!frames_dev) {
+      if (!w->copy_stream && cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return set_err(PIGO_E_CUDA, "stream creation failed");
+      CUDA_TRY(cudaStreamWaitEvent(w->copy_stream, w->ev_fork, 0));
+    }
   }
   int rot_slot = -1;
   if (angle > 0.0) {                      // core/pigo.go:232-236
@@ -349,13 +354,19 @@ int pigo_run_cascade_batch(const pigo_cascade* cc, const uint8_t* frames, int nf
     const int lane = k % lanes;
     cudaStream_t ls = lanes > 1 ? w->lane_stream[lane] : st;
     if (!frames_dev) {
+      // the copy of group k runs on the copy stream and overlaps the scan of group k-1 (pinned source memory)
       uint8_t* dst = (uint8_t*)w->frames.p + (size_t)f0 * d_stride;
       const uint8_t* src = frames + (size_t)f0 * frame_stride;
+      cudaStream_t cs = w->copy_stream;
       if (frame_stride == d_stride || nf == 1) {
-        CUDA_TRY(cudaMemcpyAsync(dst, src, nf == 1 ? frame_bytes : d_stride * (nf - 1) + frame_bytes, cudaMemcpyHostToDevice, ls));
+        CUDA_TRY(cudaMemcpyAsync(dst, src, nf == 1 ? frame_bytes : d_stride * (nf - 1) + frame_bytes, cudaMemcpyHostToDevice, cs));
       } else {
-        CUDA_TRY(cudaMemcpy2DAsync(dst, d_stride, src, frame_stride, frame_bytes, nf, cudaMemcpyHostToDevice, ls));
+        CUDA_TRY(cudaMemcpy2DAsync(dst, d_stride, src, frame_stride, frame_bytes, nf, cudaMemcpyHostToDevice, cs));
       }
+      cudaEvent_t ev = w->copy_event(k);
+      if (!ev) return set_err(PIGO_E_CUDA, "event creation failed");
+      CUDA_TRY(cudaEventRecord(ev, cs));
+      CUDA_TRY(cudaStreamWaitEvent(ls, ev, 0));
     }
     if (nscales > 0 && c->ntrees > 0) {
       ScanArgs A{};
@@ -585,6 +596,43 @@ int pigo_get_landmark_point(const pigo_puploc* p, const pigo_point* left_eye, co
   seed.row = (int)row; seed.col = (int)col; seed.scale = (float)scale; seed.perturbs = perturb;
   const uint8_t fl = flipv ? 1 : 0;
   return pigo_puploc_run(p, &seed, 1, randoms, rng_seed, pixels, rows, cols, dim, 0.0, &fl, out, PIGO_MEM_HOST, nullptr);
+}
+
+// ---- RgbToGrayscale, core/grayscale.go:8-23 ----------------------------------------------------------------
+static WorkspacePool g_gray_pool;
+
+int pigo_rgba_to_gray(const uint8_t* rgba, size_t npixels, uint8_t* gray, unsigned flags, void* stream_) {
+  if (npixels == 0) return ensure_device();
+  if (!rgba || !gray) return set_err(PIGO_E_INVALID, "null argument");
+  int rc = ensure_device();
+  if (rc) return rc;
+  WsGuard g(g_gray_pool);
+  Workspace* w = g.w;
+  if (!w) return set_err(PIGO_E_CUDA, "could not create a CUDA stream");
+  cudaStream_t st = stream_ ? (cudaStream_t)stream_ : w->stream;
+  const bool in_dev = flags & PIGO_FRAMES_DEVICE, out_dev = flags & PIGO_OUT_DEVICE;
+  const uint8_t* d_in = rgba;
+  uint8_t* d_out = gray;
+  if (!in_dev) {
+    if ((rc = w->frames.reserve(npixels * 4))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(w->frames.p, rgba, npixels * 4, cudaMemcpyHostToDevice, st));
+    d_in = (const uint8_t*)w->frames.p;
+  }
+  if (!out_dev) {
+    if ((rc = w->out.reserve(npixels))) return rc;
+    d_out = (uint8_t*)w->out.p;
+  }
+  const size_t want = (npixels / 16 + 255) / 256 + 1;
+  const int grid = (int)std::min<size_t>(want, (size_t)g_num_sms * 16);
+  timing_begin(T_GRAY, st);
+  launch_gray(d_in, npixels, d_out, grid, st);
+  timing_end(T_GRAY, st);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  if (out_dev) return PIGO_OK;
+  CUDA_TRY(cudaMemcpyAsync(gray, d_out, npixels, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return PIGO_OK;
 }
 
 }  // extern "C"

@@ -16,7 +16,7 @@ extern std::atomic<long long> g_launches;
 
 // Per-kernel CUDA-event timing (enabled by option "timing"): every launch of kernel class `slot` is bracketed by an
 // event pair on its stream; "t_<name>_ns" / "t_<name>_n" return the summed device time and the launch count.
-enum TimeSlot { T_TILED = 0, T_GATHER, T_DEEP, T_FINALIZE, T_CLUSTER, T_PUPLOC, T_NSLOTS };
+enum TimeSlot { T_TILED = 0, T_GATHER, T_DEEP, T_FINALIZE, T_CLUSTER, T_PUPLOC, T_GRAY, T_NSLOTS };
 void timing_reset();
 long long timing_query(const std::string& key);
 void timing_begin(int slot, cudaStream_t st);
@@ -98,6 +98,16 @@ struct Workspace {
   DevBuf deep[kMaxLanes], longq[kMaxLanes];   // Q1 / Q2 per pipeline lane
   cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;          // H2D copies of host frames, one event per pipeline group
+  std::vector<cudaEvent_t> copy_events;
+  cudaEvent_t copy_event(int k) {
+    while ((int)copy_events.size() <= k) {
+      cudaEvent_t e;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      copy_events.push_back(e);
+    }
+    return copy_events[k];
+  }
   int ensure_lanes(int n) {
     if (!ev_fork && cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess) return set_err(PIGO_E_CUDA, "event creation failed");
     for (int l = 0; l < n && n > 1; ++l) {
@@ -124,6 +134,8 @@ struct Workspace {
       if (ev_join[l]) cudaEventDestroy(ev_join[l]);
     }
     if (ev_fork) cudaEventDestroy(ev_fork);
+    for (auto e : copy_events) cudaEventDestroy(e);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     tiles.release(); scratch_a.release(); scratch_b.release(); scratch_c.release();
     if (pinned) cudaFreeHost(pinned);
     if (stream) cudaStreamDestroy(stream);
@@ -176,6 +188,7 @@ void launch_scan_gather(const ScanArgs& A, int grid, cudaStream_t st);
 void launch_scan_resume(const ScanArgs& A, int grid, cudaStream_t st);
 void launch_scan_tiled(const TiledArgs& A, int grid, int threads, size_t smem, int ni, cudaStream_t st);
 int tiled_max_threads(int ni);
+void launch_gray(const uint8_t* rgba, size_t npix, uint8_t* gray, int grid, cudaStream_t st);
 void launch_scan_gather2(const TiledArgs& A, int grid, size_t smem, cudaStream_t st);
 int gather2_ctas_per_sm(size_t smem);
 void launch_deep(const ScanArgs& A, unsigned long long* counter, int grid, cudaStream_t st);

@@ -301,3 +301,58 @@ def test_cpp_mirror_replays_reference_test():
     r = subprocess.run([exe, root], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "dets=4 clusters=1" in r.stdout
+
+
+def test_full_pipeline_batch_vs_oracle(gpu_face, oracle_face, sample_gray):
+    """BASELINE.json configs[4] shape: face -> cluster -> 2 pupils -> 15 landmarks per face, per frame of a batch,
+    replayed on the CPU oracle with the same injected randoms (sequencing of core/flploc_test.go:75-154)."""
+    from pigo_b200 import pipeline
+    frames = np.stack([synth.frame_faces(sample_gray, 540, 960, shift=(40 * i, 25 * i), noise_seed=30 + i) for i in range(3)])
+    cp = cp_of(None, 540, 960, 960, TEST_PARAMS)
+    plc = pigo_b200.NewPuplocCascade().UnpackCascade(pigo_b200.load_cascade("puploc"))
+    names = sorted(set(pipeline.EYE_CASCADES + pipeline.MOUTH_CASCADES))
+    flp = {n: pigo_b200.NewPuplocCascade().UnpackCascade(pigo_b200.load_cascade("lps/" + n)) for n in names}
+    oplc = O.OraclePuploc(pigo_b200.load_cascade("puploc"))
+    oflp = {n: O.OraclePuploc(pigo_b200.load_cascade("lps/" + n)) for n in names}
+
+    def randoms_for(f, call):
+        return np.random.default_rng(10_000 * f + call).random((63, 3), dtype=np.float32)
+
+    got = pipeline.detect_batch(gpu_face, plc, flp, frames, cp, iou=0.1, randoms_for=randoms_for)
+    nfaces = 0
+    for f in range(3):
+        d = oracle_face.run_cascade(frames[f], 540, 960, 960, *TEST_PARAMS, 0.0)
+        _, cl = O.cluster(d, 0.1)
+        assert [(int(x["row"]), int(x["col"]), int(x["scale"])) for x in cl] == [fc.det[:3] for fc in got[f]]
+        call = 0
+        for c, fc in zip(cl, got[f]):
+            assert np.float32(c["q"]) == np.float32(fc.det[3])
+            if c["scale"] <= 50:
+                continue
+            nfaces += 1
+            ls, rs = pipeline.eye_seeds(int(c["row"]), int(c["col"]), int(c["scale"]), 50)
+            le = oplc.run_detector(ls.Row, ls.Col, ls.Scale, 50, randoms_for(f, call), frames[f], 540, 960, 960)
+            re_ = oplc.run_detector(rs.Row, rs.Col, rs.Scale, 50, randoms_for(f, call + 1), frames[f], 540, 960, 960)
+            call += 2
+            assert (fc.left_eye.Row, fc.left_eye.Col, np.float32(fc.left_eye.Scale)) == (le[0], le[1], le[2])
+            assert (fc.right_eye.Row, fc.right_eye.Col, np.float32(fc.right_eye.Scale)) == (re_[0], re_[1], re_[2])
+            for (name, flip), lm in zip(pipeline.landmark_calls(), fc.landmarks):
+                r0, c0, s0 = O.landmark_seed(le[0], le[1], re_[0], re_[1])
+                e = oflp[name].run_detector(r0, c0, float(s0), 63, randoms_for(f, call), frames[f], 540, 960, 960, 0.0, flip)
+                call += 1
+                assert (lm.Row, lm.Col, np.float32(lm.Scale)) == (e[0], e[1], e[2])
+    assert nfaces >= 3
+
+
+def test_rgb_to_grayscale_matches_oracle():
+    """core/grayscale.go:8-23 on NRGBA pixels (section 8f row N2): float64 luma of the 16-bit expanded, alpha-premultiplied
+    channels, truncated to uint8 -- bit-exact against both CPU restatements, opaque and translucent pixels, ragged sizes."""
+    rng = np.random.default_rng(4)
+    for shape in [(1080, 1920), (37, 53), (1, 1), (3, 5)]:
+        rgba = rng.integers(0, 256, size=shape + (4,), dtype=np.uint8)
+        if shape[0] > 100:
+            rgba[..., 3] = 255
+        g = pigo_b200.RgbToGrayscale(rgba)
+        assert g.shape == shape and g.dtype == np.uint8
+        assert np.array_equal(g, O.rgba_to_gray(rgba))
+    assert pigo_b200.RgbToGrayscale(np.zeros((0, 0, 4), np.uint8)).size == 0
