@@ -112,7 +112,11 @@ struct TiledArgs {
   uint32_t gather_blocks_per_frame;       // 16x16-window blocks of those scales (ScaleEntry.pad = block prefix)
   unsigned long long* gather_counter;
   unsigned long long* q1_counter;         // consumer cursor of Q1 (gather-v2 kernel only)
-  int32_t consume_q1;
+  unsigned int* tile_done_counter;        // fused kernel: tile warps that have left their tile loop
+  uint32_t total_tile_warps;
+  int32_t tile_warps_join_gather;         // tile warps that ran out of tiles take gather blocks
+  int32_t pad4;
+  int32_t consume_q1;                     // 0 never, 1 Q1 final at launch (gather-v2), 2 final when all tile warps are done
   int32_t gather_ni;                      // windows per lane in the gather role (ILP)
 };
 

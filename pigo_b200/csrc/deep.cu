@@ -10,15 +10,21 @@
 
 namespace pigo {
 
+// GROUP = lanes (= trees per step) per window: 32 -> one window per warp; 16 -> two windows per warp, each half-warp
+// an independent 16-lane group (all sync ops use the half's mask), which halves the speculation past the rejecting
+// tree and doubles the windows in flight per warp.
+template <int GROUP>
 __global__ void __launch_bounds__(256) deep_kernel(const ScanArgs A, unsigned long long* counter) {
-  const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  const int sub = lane & (GROUP - 1);
+  const unsigned gmask = GROUP == 32 ? 0xffffffffu : (0xffffu << (lane & 16));
+  const int leader = lane & ~(GROUP - 1);
   const FaceTables T = A.tab;
   const uint32_t qn = min(*A.long_count, A.long_cap);
   for (;;) {
     unsigned long long g = 0;
-    if (lane == 0) g = atomicAdd(counter, 1ull);
-    g = __shfl_sync(FULL, g, 0);
+    if (sub == 0) g = atomicAdd(counter, 1ull);
+    g = __shfl_sync(gmask, g, leader);
     if (g >= qn) break;
     const DeepItem it = A.longq[g];
     const int si = find_scale(A.plan, A.nscales, it.wid);
@@ -32,7 +38,7 @@ __global__ void __launch_bounds__(256) deep_kernel(const ScanArgs A, unsigned lo
     bool rejected = false;
     float thr_prev = 0.f;
     while (t0 < T.ntrees && !rejected) {
-      const int t = min(t0 + lane, T.ntrees - 1);     // lanes past the last tree redo it harmlessly
+      const int t = min(t0 + sub, T.ntrees - 1);      // lanes past the last tree redo it harmlessly
       const int* tc = reinterpret_cast<const int*>(T.codes + (size_t)t * 256);
       int idx = 1;
 #pragma unroll
@@ -45,15 +51,15 @@ __global__ void __launch_bounds__(256) deep_kernel(const ScanArgs A, unsigned lo
       }
       const float pred = __ldg(T.preds + (size_t)t * 64 + idx - 64);
       const float thr = __ldg(T.thresh + t);
-      const int nvalid = min(32, T.ntrees - t0);
+      const int nvalid = min(GROUP, T.ntrees - t0);
       for (int j = 0; j < nvalid; ++j) {              // the reference's sequential accumulation, :137-141
-        acc += __shfl_sync(FULL, pred, j);
-        thr_prev = __shfl_sync(FULL, thr, j);
+        acc += __shfl_sync(gmask, pred, leader + j);
+        thr_prev = __shfl_sync(gmask, thr, leader + j);
         if (acc <= thr_prev) { rejected = true; break; }
       }
-      t0 += 32;
+      t0 += GROUP;
     }
-    if (!rejected && lane == 0) {
+    if (!rejected && sub == 0) {
       const float q = acc - thr_prev;                 // :144 (thr_prev == threshold of the last tree)
       if (q > 0.0f) {                                 // :246
         const int pos = atomicAdd(A.raw_count + it.frame, 1);
@@ -63,7 +69,10 @@ __global__ void __launch_bounds__(256) deep_kernel(const ScanArgs A, unsigned lo
   }
 }
 
-void launch_deep(const ScanArgs& A, unsigned long long* counter, int grid, cudaStream_t st) { deep_kernel<<<grid, 256, 0, st>>>(A, counter); }
+void launch_deep(const ScanArgs& A, unsigned long long* counter, int grid, int group, cudaStream_t st) {
+  if (group == 16) deep_kernel<16><<<grid, 256, 0, st>>>(A, counter);
+  else deep_kernel<32><<<grid, 256, 0, st>>>(A, counter);
+}
 
 // ---- v2: the cascade tail [kd, ntrees) resident in shared memory (one persistent CTA per SM) ----------------------
 // Every item in Q2 sits at tree >= kd, so node codes, leaves and thresholds never leave the SM; only the 12 pixel

@@ -1,7 +1,8 @@
 // scan_driver.cu -- host-side planning and sequencing of the scan kernels for one RunCascade batch:
-//   tiled kernel  : scales grouped into bands whose pixel tiles fit a per-warp shared-memory buffer
-//   gather kernel : the remaining (large) scales, every scale of the rotated path, non-depth-6 cascades
-//   resume kernel : finishes the long-lived windows the tiled kernel parked in the deep queue
+//   fused kernel     : tile warps (scales whose pixel tiles fit a per-warp shared-memory buffer) + gather warps (the rest)
+//   gather-v2 kernel : the straggler queue Q1 (and any blocks the fused kernel did not take)
+//   deep kernel      : queue Q2, one warp (or half warp) per window, 32 (16) trees per step
+//   gather kernel    : universal fallback -- rotated scan, cascades of depth != 6, scan_mode=1
 #include <algorithm>
 #include <cstring>
 
@@ -157,6 +158,8 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
   T.tab_tiled = (const uint8_t*)c->tiled_tab.p;
   T.gather_counter = d_work;
   T.q1_counter = d_work + 2;
+  T.tile_done_counter = (unsigned int*)(d_work + 7);
+  T.total_tile_warps = 0;
   T.gather_scale_lo = 0;
   T.gather_blocks_per_frame = 0;
   T.gather_ni = (int)std::min<long long>(std::max<long long>(1, g_opt.gather_ni.load()), 3);
@@ -190,7 +193,9 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
         F.tiles_per_frame = tp.tiles_per_frame;
         F.total_tiles = (unsigned long long)tp.tiles_per_frame * A.nframes;
         F.tile_warps = W;
-        F.consume_q1 = 0;
+        F.consume_q1 = g_opt.fused_q1.load() ? 2 : 0;
+        F.tile_warps_join_gather = g_opt.fused_switch.load() ? 1 : 0;
+        F.tile_done_counter = (unsigned int*)(d_work + 7);
         first_untiled = tp.first_untiled;
         if (Wg > 0 && first_untiled < A.nscales) {
           if ((rc = upload_block_prefix(w, first_untiled, A.nscales, st, &F.gather_blocks_per_frame))) return rc;
@@ -203,6 +208,7 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
         long long grid = num_sms;
         if (Wg == 0) grid = std::max<long long>(1, std::min<long long>(num_sms, (long long)((F.total_tiles + W - 1) / W)));
         const size_t smem = tiles0 + (size_t)tile_bytes * W;
+        F.total_tile_warps = (uint32_t)grid * (uint32_t)W;
         timing_begin(T_TILED, st);
         launch_scan_tiled(F, (int)grid, (W + Wg) * 32, smem, ni, st);
         timing_end(T_TILED, st);
@@ -228,8 +234,10 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
       min_handover_tree = std::min(min_handover_tree, G.ks);
       const size_t smem = ((384 + (size_t)G.ks * 516 + 127) & ~(size_t)127);
       int per_sm = (int)g_opt.gather_ctas_per_sm.load();
-      const int occ = gather2_ctas_per_sm(smem);
+      const int occ = gather2_ctas_per_sm(smem, G.gather_ni);
       if (per_sm <= 0 || per_sm > occ) per_sm = occ;
+      const int tail_lim = (int)g_opt.tail_ctas_per_sm.load();
+      if (tail_lim > 0) per_sm = std::min(per_sm, tail_lim);
       timing_begin(T_GATHER, st);
       launch_scan_gather2(G, num_sms * per_sm, smem, st);
       timing_end(T_GATHER, st);
@@ -245,7 +253,10 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
     const size_t tail_bytes = (size_t)(A.tab.ntrees - kd) * 516 + 16;
     timing_begin(T_DEEP, st);
     if (g_opt.deep_smem.load() && tail_bytes + 128 <= kSmemPerCta) launch_deep_smem(A, d_work + 3, (const uint8_t*)c->tiled_tab.p, kd, num_sms, st);
-    else launch_deep(A, d_work + 3, num_sms * 8, st);
+    else {
+      const int tail_lim = (int)g_opt.tail_ctas_per_sm.load();
+      launch_deep(A, d_work + 3, num_sms * (tail_lim > 0 ? std::min(8, tail_lim) : 8), (int)g_opt.deep_group.load(), st);
+    }
     timing_end(T_DEEP, st);
     g_launches++;
     if ((rc = check_launch("deep scan"))) return rc;

@@ -8,9 +8,8 @@
 // warps stay full although ~60% of windows die at the first tree.  Windows are handed out in chunks
 // of `chunk` consecutive in-frame indices through one global atomic per chunk.
 //
-// The tiled kernel (scan_tiled.cu) takes the small scales; this kernel covers the scales in
-// [scale_lo, scale_hi) -- large windows whose s x s footprint does not fit a shared-memory tile --
-// and every scale of the rotated path.
+// This is the universal path: every scale of the rotated scan (angle > 0), cascades whose tree depth is not 6, and
+// scan_mode=1.  The unrotated depth-6 scan uses the fused kernel of scan_tiled.cu (+ gather-v2 and deep kernels).
 #include "common.cuh"
 #include "host.h"
 
@@ -57,9 +56,7 @@ __device__ __forceinline__ int walk_tree_rot(const int8_t* __restrict__ tc, cons
   return idx;
 }
 
-// QUEUE = false: windows of the ladder entries [scale_lo, scale_hi) of every frame, in chunks.
-// QUEUE = true : resumes the DeepItems the tiled kernel handed over (wid, frame, tree, partial score).
-template <int DEPTH, bool ROT, bool QUEUE>
+template <int DEPTH, bool ROT>
 __global__ void __launch_bounds__(256) scan_gather_kernel(const ScanArgs A) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -71,12 +68,7 @@ __global__ void __launch_bounds__(256) scan_gather_kernel(const ScanArgs A) {
   const uint32_t w_lo = A.plan[A.scale_lo].wbase;
   const uint32_t w_hi = (A.scale_hi < A.nscales) ? A.plan[A.scale_hi].wbase : A.wins_per_frame;
 
-  unsigned long long total_chunks = (unsigned long long)A.chunks_per_frame * A.nframes;
-  uint32_t qn = 0;
-  if (QUEUE) {
-    qn = min(*A.deep_count, A.deep_cap);
-    total_chunks = (qn + 31u) / 32u;
-  }
+  const unsigned long long total_chunks = (unsigned long long)A.chunks_per_frame * A.nframes;
 
   // per-lane item
   bool alive = false;
@@ -97,28 +89,16 @@ __global__ void __launch_bounds__(256) scan_gather_kernel(const ScanArgs A) {
         if (lane == 0) g = atomicAdd(A.chunk_counter, 1ull);
         g = __shfl_sync(FULL, g, 0);
         if (g >= total_chunks) { more = false; break; }
-        if (QUEUE) {
-          cur = (uint32_t)g * 32u;
-          end = min(cur + 32u, qn);
-        } else {
-          cframe = (int)(g / A.chunks_per_frame);
-          const uint32_t k = (uint32_t)(g % A.chunks_per_frame);
-          cur = w_lo + k * A.chunk;
-          end = min(cur + A.chunk, w_hi);
-        }
+        cframe = (int)(g / A.chunks_per_frame);
+        const uint32_t k = (uint32_t)(g % A.chunks_per_frame);
+        cur = w_lo + k * A.chunk;
+        end = min(cur + A.chunk, w_hi);
         continue;
       }
       const uint32_t avail = end - cur;
       const uint32_t rank = __popc(need & lanemask_lt());
       if (!alive && rank < avail) {
-        int t0 = 0;
-        float acc0 = 0.f;
-        if (QUEUE) {
-          const DeepItem it = A.deep[cur + rank];
-          wid = it.wid; cframe = it.frame; t0 = it.tree; acc0 = it.acc;
-        } else {
-          wid = cur + rank;
-        }
+        wid = cur + rank;
         const int si = find_scale(A.plan, A.nscales, wid);
         const ScaleEntry e = A.plan[si];
         const uint32_t local = wid - e.wbase;
@@ -130,8 +110,8 @@ __global__ void __launch_bounds__(256) scan_gather_kernel(const ScanArgs A) {
         frame = cframe;
         const uint8_t* fb = A.frames + (size_t)cframe * A.frame_stride;
         pc = ROT ? fb : fb + (size_t)r * A.dim + c;
-        t = t0;
-        acc = acc0;
+        t = 0;
+        acc = 0.f;
         alive = true;
       }
       cur += min((uint32_t)__popc(need), avail);
@@ -167,16 +147,13 @@ __global__ void __launch_bounds__(256) scan_gather_kernel(const ScanArgs A) {
 void launch_scan_gather(const ScanArgs& A, int grid, cudaStream_t st) {
   const bool rot = A.rot_slot >= 0;
   if (A.tab.depth == 6) {
-    if (rot) scan_gather_kernel<6, true, false><<<grid, 256, 0, st>>>(A);
-    else scan_gather_kernel<6, false, false><<<grid, 256, 0, st>>>(A);
+    if (rot) scan_gather_kernel<6, true><<<grid, 256, 0, st>>>(A);
+    else scan_gather_kernel<6, false><<<grid, 256, 0, st>>>(A);
   } else {
-    if (rot) scan_gather_kernel<0, true, false><<<grid, 256, 0, st>>>(A);
-    else scan_gather_kernel<0, false, false><<<grid, 256, 0, st>>>(A);
+    if (rot) scan_gather_kernel<0, true><<<grid, 256, 0, st>>>(A);
+    else scan_gather_kernel<0, false><<<grid, 256, 0, st>>>(A);
   }
 }
-
-// Finishes the windows parked in the deep queue (unrotated depth-6 cascades only: the tiled kernel's domain).
-void launch_scan_resume(const ScanArgs& A, int grid, cudaStream_t st) { scan_gather_kernel<6, false, true><<<grid, 256, 0, st>>>(A); }
 
 }  // namespace pigo
 
@@ -184,8 +161,8 @@ namespace pigo {
 int gather_max_ctas_per_sm(int depth, bool rot) {
   int n = 0;
   const void* f;
-  if (depth == 6) f = rot ? (const void*)scan_gather_kernel<6, true, false> : (const void*)scan_gather_kernel<6, false, false>;
-  else f = rot ? (const void*)scan_gather_kernel<0, true, false> : (const void*)scan_gather_kernel<0, false, false>;
+  if (depth == 6) f = rot ? (const void*)scan_gather_kernel<6, true> : (const void*)scan_gather_kernel<6, false>;
+  else f = rot ? (const void*)scan_gather_kernel<0, true> : (const void*)scan_gather_kernel<0, false>;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, f, 256, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 4; }
   return n;
 }

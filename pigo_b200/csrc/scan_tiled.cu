@@ -1,21 +1,22 @@
-// scan_tiled.cu -- the hot kernel: RunCascade's (scale,row,col) grid (core/pigo.go:226-249) with classifyRegion
-// (core/pigo.go:113-147) for the small and medium scales, ONE WARP PER IMAGE TILE.
+// scan_tiled.cu -- the hot kernels of RunCascade's (scale,row,col) grid (core/pigo.go:226-249) with classifyRegion
+// (core/pigo.go:113-147): the warp-specialised FUSED kernel (tile warps + gather warps) and the gather-v2 kernel.
 //
-//  * Persistent CTA (one per SM), W independent warps.  The first KS trees of the cascade (codes, leaves,
-//    threshold: one 516-byte record per tree, 129 words so consecutive trees are skewed by one bank) are staged
-//    ONCE per CTA into shared memory by the TMA bulk engine (cp.async.bulk + mbarrier).
-//  * Each warp owns a private pixel-tile buffer in shared memory.  A tile is an image region (core + halo) that
-//    serves EVERY scale of a band (e.g. 20..39 px) at once, so the frame is read from L2/HBM once per band rather
-//    than once per scale; it is filled with 16-byte cp.async vector loads (coalesced 128-bit rows).
-//  * Windows whose centre lies in the tile's core are evaluated one-per-lane with LANE REFILL: every iteration
-//    each live lane walks ONE tree (6 levels: 1 LDS.32 for the node's 4 codes, 2 LDS.U8 pixel gathers); lanes
-//    whose window was rejected are re-armed with the next window of the tile via ballot+popc, so warps stay full
-//    although ~60% of the windows die at tree 0.  NI independent item slots per lane give the ILP that hides the
-//    shared-memory latency with only W warps per SM.
-//  * Long-lived windows must not pin a tile: a window that reaches tree KS, and whatever is still alive when
-//    fewer than `tail_min` items remain after the tile's windows ran out, is appended (wid, frame, tree, score)
-//    to the global "deep" queue and finished by the resume kernel.  If the queue is full the lane simply keeps
-//    going (cascade rows beyond KS are then read from global memory), so the queue is an optimisation only.
+//  * Fused kernel: persistent CTA (one per SM).  The first KS trees of the cascade (codes, leaves, threshold: one
+//    516-byte record per tree, 129 words so consecutive trees are skewed by one bank) are staged ONCE per CTA into
+//    shared memory by the TMA bulk engine (cp.async.bulk + mbarrier).
+//  * TILE WARPS, one warp per image tile: each warp owns a private pixel-tile buffer in shared memory.  A tile is an
+//    image region (core + halo) that serves EVERY scale of a band (20..39 px) at once, so the frame is read from
+//    L2/HBM once per band rather than once per scale; it is filled by one TMA bulk copy per (16-byte aligned) tile row
+//    completing on the warp's own mbarrier.  Windows whose centre lies in the tile's core are evaluated one-per-lane
+//    with LANE REFILL: every iteration each live lane walks ONE tree (6 levels: 1 LDS.32 for the node's 4 codes,
+//    2 LDS.U8 pixel gathers); lanes whose window was rejected are re-armed with the next window of the tile via
+//    ballot+popc (straight-line fast path), so warps stay full although ~60% of the windows die at tree 0.
+//  * Long-lived windows must not pin a tile: whatever is still alive when fewer than `tail_min` windows remain after
+//    the tile's list ran out goes to the straggler queue Q1 (finished one-per-lane by gather-v2), and a window that
+//    survives the KS resident trees goes to Q2 (finished one-per-WARP, 32/16 trees per step, by deep.cu).  If a queue
+//    is full the lane simply keeps walking (rows beyond KS from global memory): queues are an optimisation only.
+//  * GATHER WARPS (same CTA, same shared cascade prefix): the scales too large for a per-warp tile, in 16x16-window
+//    blocks, pixels by ld.global.nc.
 //
 // Scores are float32 sums in tree order and the result is bit-identical to the reference.
 #include "common.cuh"
@@ -76,10 +77,15 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
   const ScanArgs& S = A.scan;
   const FaceTables T = S.tab;
   const unsigned long long total_blocks = (unsigned long long)A.gather_blocks_per_frame * S.nframes;
-  const uint32_t q1n = A.consume_q1 ? min(*S.deep_count, S.deep_cap) : 0u;
-  bool q1_more = q1n > 0;
+  // consume_q1: 0 = never, 1 = Q1 is complete when this kernel starts (gather-v2), 2 = fused kernel: Q1 becomes
+  // readable once EVERY tile warp of the grid has left its tile loop (tile_done_counter == total_tile_warps)
+  uint32_t q1n = A.consume_q1 == 1 ? min(*S.deep_count, S.deep_cap) : 0u;
+  bool q1_more = q1n > 0, blocks_more = total_blocks > 0, q1_late_checked = A.consume_q1 != 2;
   bool from_q1 = false;
-  if (total_blocks == 0 && !q1_more) return;
+  // In the fused kernel a warp drains at most a few chunks: whoever arrives last must not serialise the whole queue
+  // on one warp -- what is left is picked up by the full-grid gather-v2 launch that follows.
+  int q1_budget = A.consume_q1 == 2 ? 4 : 0x7fffffff;
+  if (!blocks_more && !q1_more && q1_late_checked) return;
   const uint32_t tbo_last = casc + (uint32_t)T.ntrees * kTreeRec;   // record offset "one past the last tree"
 
   // NG independent windows per lane: their dependent LDS -> L2 gather chains overlap (ILP), which is what hides the
@@ -105,7 +111,8 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
       while (need && more) {
         if (cur == end) {
           unsigned long long g = 0;
-          if (q1_more) {                       // stragglers first: 32 queue items per grab
+          if (q1_more && q1_budget-- <= 0) q1_more = false;
+          if (q1_more) {                       // stragglers: 32 queue items per grab
             if (lane == 0) g = atomicAdd(A.q1_counter, 1ull);
             g = __shfl_sync(FULL, g, 0);
             if (g * 32ull < q1n) {
@@ -116,10 +123,30 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
             q1_more = false;
           }
           from_q1 = false;
-          if (total_blocks == 0) { more = false; break; }
-          if (lane == 0) g = atomicAdd(A.gather_counter, 1ull);
-          g = __shfl_sync(FULL, g, 0);
-          if (g >= total_blocks) { more = false; break; }
+          if (blocks_more) {
+            if (lane == 0) g = atomicAdd(A.gather_counter, 1ull);
+            g = __shfl_sync(FULL, g, 0);
+            if (g >= total_blocks) blocks_more = false;
+          }
+          if (!blocks_more) {
+            if (!q1_late_checked) {
+              // fused kernel, out of blocks: if every tile warp has finished, the straggler queue is final -- drain it
+              q1_late_checked = true;
+              unsigned done = 0;
+              if (lane == 0) done = atomicAdd(A.tile_done_counter, 0u);
+              done = __shfl_sync(FULL, done, 0);
+              if (done == A.total_tile_warps) {
+                __threadfence();
+                unsigned n = 0;
+                if (lane == 0) n = atomicAdd(S.deep_count, 0u);
+                q1n = min(__shfl_sync(FULL, n, 0), S.deep_cap);
+                q1_more = q1n > 0;
+                if (q1_more) continue;
+              }
+            }
+            more = false;
+            break;
+          }
           cframe = (int)(g / A.gather_blocks_per_frame);
           const uint32_t bidx = (uint32_t)(g % A.gather_blocks_per_frame);
           int lo = A.gather_scale_lo, hi = S.nscales - 1;   // ladder entry whose block range contains bidx
@@ -274,15 +301,14 @@ __device__ __forceinline__ void stage_cascade(const TiledArgs& A, uint32_t smem_
 
 // gather-v2: every warp plays the gather role (untiled scales in 16x16-window blocks + the Q1 stragglers), with the
 // cascade prefix in shared memory.  256 threads, several CTAs per SM.
-__global__ void __launch_bounds__(256, 4) scan_gather2_kernel(const TiledArgs A) {
+template <int NG, int MINB>
+__global__ void __launch_bounds__(256, MINB) scan_gather2_kernel(const TiledArgs A) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
   const uint32_t casc = kCascOff;
   const uint32_t casc_bytes = (uint32_t)A.ks * kTreeRec;
   stage_cascade(A, smem_base, casc, (casc_bytes + 15u) & ~15u);
-  if (A.gather_ni >= 3) gather_role<3>(A, smem, casc, casc + casc_bytes);
-  else if (A.gather_ni == 2) gather_role<2>(A, smem, casc, casc + casc_bytes);
-  else gather_role<1>(A, smem, casc, casc + casc_bytes);
+  gather_role<NG>(A, smem, casc, casc + casc_bytes);
 }
 
 template <int NI, int MAXT>
@@ -569,6 +595,16 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
       }
     }
   }
+
+  // ---- out of tiles: announce it (the straggler queue is final once every tile warp has), then help the gather role
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();
+    atomicAdd(A.tile_done_counter, 1u);
+  }
+  if (!A.tile_warps_join_gather) return;
+  if (A.gather_ni >= 2) gather_role<2>(A, smem, casc, casc_end);
+  else gather_role<1>(A, smem, casc, casc_end);
 }
 
 template <int NI, int MAXT>
@@ -577,14 +613,22 @@ static void launch_tiled_ni(const TiledArgs& A, int grid, int threads, size_t sm
   scan_tiled_kernel<NI, MAXT><<<grid, threads, smem, st>>>(A);
 }
 
-void launch_scan_gather2(const TiledArgs& A, int grid, size_t smem, cudaStream_t st) {
-  cudaFuncSetAttribute(scan_gather2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  scan_gather2_kernel<<<grid, 256, smem, st>>>(A);
+static const void* gather2_fn(int ng) {
+  if (ng >= 3) return (const void*)scan_gather2_kernel<3, 4>;
+  if (ng == 2) return (const void*)scan_gather2_kernel<2, 4>;
+  return (const void*)scan_gather2_kernel<1, 6>;
 }
-int gather2_ctas_per_sm(size_t smem) {
+void launch_scan_gather2(const TiledArgs& A, int grid, size_t smem, cudaStream_t st) {
+  const void* fn = gather2_fn(A.gather_ni);
+  cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  void* args[] = {(void*)&A};
+  cudaLaunchKernel(fn, dim3(grid), dim3(256), args, smem, st);
+}
+int gather2_ctas_per_sm(size_t smem, int ng) {
   int n = 0;
-  cudaFuncSetAttribute(scan_gather2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan_gather2_kernel, 256, smem) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
+  const void* fn = gather2_fn(ng);
+  cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, 256, smem) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
   return n;
 }
 

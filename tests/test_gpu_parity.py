@@ -252,6 +252,8 @@ VARIANTS = [
     {"scan_mode": 0, "gather_warps": 24, "tile_warps": 8, "tile_ni": 1, "tile_ks": 32},
     {"scan_mode": 3, "gather_ks": 32, "gather_ni": 1, "sub_batch": 2, "lanes": 2},      # gather-v2 + deep kernel only
     {"scan_mode": 0, "gather_ni": 3, "sub_batch": 1, "lanes": 3, "deep_smem": 1},
+    {"scan_mode": 0, "deep_group": 32, "tile_ks": 8, "gather_ks": 8, "fused_switch": 1, "fused_q1": 1},
+    {"scan_mode": 0, "fused_switch": 1, "fused_q1": 0, "tile_tail_min": 33},
     {"scan_mode": 3, "gather_ks": 4},                                                   # nearly everything through the deep kernel
     {"scan_mode": 0, "gather_ks": 468, "tile_ks": 468, "tile_warps": 4, "gather_warps": 0},   # whole cascade resident: no Q2
 ]
@@ -260,7 +262,7 @@ VARIANTS = [
 @pytest.fixture
 def restore_options():
     keys = ["scan_mode", "tile_ni", "tile_warps", "tile_ks", "tile_tail_min", "tile_band_ratio", "tile_max_scale", "chunk",
-            "gather_warps", "gather_ks", "gather_ni", "sub_batch", "lanes", "deep_smem"]
+            "gather_warps", "gather_ks", "gather_ni", "sub_batch", "lanes", "deep_smem", "deep_group", "fused_switch", "fused_q1"]
     saved = {k: pigo_b200.get_option(k) for k in keys}
     yield
     for k, v in saved.items():
