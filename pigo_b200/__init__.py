@@ -382,6 +382,17 @@ class FlpCascade:
         return self.PuplocCascade.GetLandmarkPoint(*a, **k)
 
 
+def landmark_seed_host(leftEye: Puploc, rightEye: Puploc, perturb: int) -> Puploc:
+    """The float64 seed arithmetic of GetLandmarkPoint (core/flploc.go:37-50), for batching several calls into one launch."""
+    import math
+    dx = (leftEye.Row - rightEye.Row) ** 2
+    dy = (leftEye.Col - rightEye.Col) ** 2
+    dist = math.sqrt(float(dx + dy))
+    row = float(leftEye.Row + rightEye.Row) / 2.0 + 0.25 * dist
+    col = float(leftEye.Col + rightEye.Col) / 2.0 + 0.15 * dist
+    return Puploc(int(row), int(col), float(np.float32(3.0 * dist)), perturb)
+
+
 def RgbToGrayscale(rgba: np.ndarray) -> np.ndarray:
     """pigo.RgbToGrayscale, core/grayscale.go:8-23, for an NRGBA pixel array [..., 4] (R, G, B, A); returns uint8 [...]."""
     a = np.ascontiguousarray(rgba, dtype=np.uint8)

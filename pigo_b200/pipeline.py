@@ -45,27 +45,47 @@ def landmark_calls():
 def detect_batch(clf: Pigo, plc: PuplocCascade, flpcs: Dict[str, PuplocCascade], frames: np.ndarray, cp: CascadeParams,
                  iou: float = 0.1, min_face: int = 50, eye_perturbs: int = 50, flp_perturbs: int = 63,
                  randoms_for: Optional[Callable[[int, int], np.ndarray]] = None) -> List[List[Face]]:
+    """Per frame: one batched RunCascade for all frames, ClusterDetections, then ONE RunDetector launch for the eye seeds
+    of all faces of the frame and ONE launch per (landmark cascade) for all faces and both flips -- the per-call results
+    are identical to calling GetLandmarkPoint face by face (each seed carries its own randoms / RNG key)."""
+    from . import landmark_seed_host
     frames = np.ascontiguousarray(frames, dtype=np.uint8)
     dets, cnt = clf.RunCascadeBatch(frames, cp, 0.0)
     out: List[List[Face]] = []
+    calls = landmark_calls()
     for f in range(frames.shape[0]):
         img = ImageParams(frames[f], cp.ImageParams.Rows, cp.ImageParams.Cols, cp.ImageParams.Dim)
         _, clusters = clf.cluster_array(dets[f, :cnt[f]].copy(), iou)
-        faces, call = [], 0
-        for c in clusters:
-            face = Face((int(c["row"]), int(c["col"]), int(c["scale"]), float(c["q"])))
-            if c["scale"] > min_face:
+        faces = [Face((int(c["row"]), int(c["col"]), int(c["scale"]), float(c["q"]))) for c in clusters]
+        big = [k for k, c in enumerate(clusters) if c["scale"] > min_face]
+        # call indices follow the reference's sequential order: per face 2 eye calls, then the 15 landmark calls
+        base = {k: i * (2 + len(calls)) for i, k in enumerate(big)}
+        if big:
+            seeds, rnds = [], []
+            for k in big:
+                c = clusters[k]
                 ls, rs = eye_seeds(int(c["row"]), int(c["col"]), int(c["scale"]), eye_perturbs)
-                rl = randoms_for(f, call) if randoms_for else None
-                rr = randoms_for(f, call + 1) if randoms_for else None
-                rnd = np.stack([rl, rr]) if randoms_for else None
-                face.left_eye, face.right_eye = plc.run_detector_batch([ls, rs], img, 0.0, [False, False], rnd, rng_seed=1000 * f + call)
-                call += 2
-                for name, flip in landmark_calls():
-                    rnd = randoms_for(f, call) if randoms_for else None
-                    face.landmarks.append(flpcs[name].GetLandmarkPoint(face.left_eye, face.right_eye, img, flp_perturbs, flip,
-                                                                      randoms=rnd, rng_seed=1000 * f + call))
-                    call += 1
-            faces.append(face)
+                seeds += [ls, rs]
+                if randoms_for:
+                    rnds += [randoms_for(f, base[k]), randoms_for(f, base[k] + 1)]
+            eyes = plc.run_detector_batch(seeds, img, 0.0, [False] * len(seeds), np.stack(rnds) if randoms_for else None, rng_seed=1000 * f)
+            for i, k in enumerate(big):
+                faces[k].left_eye, faces[k].right_eye = eyes[2 * i], eyes[2 * i + 1]
+                faces[k].landmarks = [None] * len(calls)
+            for name in sorted(set(n for n, _ in calls)):
+                seeds, flips, rnds, where = [], [], [], []
+                for k in big:
+                    for ci, (n, flip) in enumerate(calls):
+                        if n != name:
+                            continue
+                        seeds.append(landmark_seed_host(faces[k].left_eye, faces[k].right_eye, flp_perturbs))
+                        flips.append(flip)
+                        where.append((k, ci))
+                        if randoms_for:
+                            rnds.append(randoms_for(f, base[k] + 2 + ci))
+                pts = flpcs[name].run_detector_batch(seeds, img, 0.0, flips, np.stack(rnds) if randoms_for else None,
+                                                     rng_seed=1000 * f + 7)
+                for (k, ci), p in zip(where, pts):
+                    faces[k].landmarks[ci] = p
         out.append(faces)
     return out
