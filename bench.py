@@ -194,12 +194,12 @@ def main():
         return float(t.item())
 
     # ---- device-resident throughput ("value")
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()   # nvidia-smi samples every 100 ms: started before the warm-up so the short timed region is covered
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    sampler = ClockSampler(dev)
-    if rank == 0:
-        sampler.start()
     launches0 = pigo_b200.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -210,6 +210,9 @@ def main():
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = pigo_b200.launch_count() - launches0
+    for _ in range(args.steps):   # keep the GPU under the same load while the sampler collects a few more points
+        step_device()
+    torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = W * nf * world / (ms_step * 1e-3)

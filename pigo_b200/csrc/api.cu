@@ -72,6 +72,19 @@ long long timing_query(const std::string& key) {
   return -1;
 }
 
+// A workspace can be handed to another caller (another thread / stream) while the asynchronous work of its previous
+// user is still running on that user's stream: order every new user behind the last recorded use.
+static int ws_enter(Workspace* w, cudaStream_t st) {
+  if (!w->busy && cudaEventCreateWithFlags(&w->busy, cudaEventDisableTiming) != cudaSuccess) return set_err(PIGO_E_CUDA, "event creation failed");
+  if (w->busy_valid && cudaStreamWaitEvent(st, w->busy, 0) != cudaSuccess) return set_err(PIGO_E_CUDA, "cudaStreamWaitEvent failed");
+  return PIGO_OK;
+}
+static int ws_leave_async(Workspace* w, cudaStream_t st) {
+  if (cudaEventRecord(w->busy, st) != cudaSuccess) return set_err(PIGO_E_CUDA, "cudaEventRecord failed");
+  w->busy_valid = true;
+  return PIGO_OK;
+}
+
 int set_err(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -281,6 +294,7 @@ int pigo_run_cascade_batch(const pigo_cascade* cc, const uint8_t* frames, int nf
   Workspace* w = g.w;
   if (!w) return set_err(PIGO_E_CUDA, "could not create a CUDA stream");
   cudaStream_t st = stream_ ? (cudaStream_t)stream_ : w->stream;
+  if ((rc = ws_enter(w, st))) return rc;
 
   // plan (cached per workspace)
   if (w->p_rows != rows || w->p_cols != cols || w->p_min != min_size || w->p_max != max_size || w->p_shift != shift_factor ||
@@ -391,7 +405,7 @@ int pigo_run_cascade_batch(const pigo_cascade* cc, const uint8_t* frames, int nf
   g_launches++;
   CUDA_TRY(cudaGetLastError());
 
-  if (out_dev) return PIGO_OK;
+  if (out_dev) return ws_leave_async(w, st);
   CUDA_TRY(cudaMemcpyAsync(n_out, d_nout, (size_t)nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   int need_more = 0;
@@ -432,6 +446,7 @@ int pigo_cluster_batch(pigo_det* dets, const int* n, int nframes, int cap_per_fr
   Workspace* w = g.w;
   if (!w) return set_err(PIGO_E_CUDA, "could not create a CUDA stream");
   cudaStream_t st = stream_ ? (cudaStream_t)stream_ : w->stream;
+  if ((rc = ws_enter(w, st))) return rc;
   const int cap = std::max(cap_per_frame, 1), ocap = std::max(out_cap_per_frame, 1);
   const size_t nd = (size_t)nframes * cap;
   if ((rc = w->scratch_a.reserve(nd * sizeof(pigo_det)))) return rc;
@@ -457,7 +472,7 @@ int pigo_cluster_batch(pigo_det* dets, const int* n, int nframes, int cap_per_fr
   timing_end(T_CLUSTER, st);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
-  if (dev) return PIGO_OK;
+  if (dev) return ws_leave_async(w, st);
   if (cap_per_frame > 0 && dets) CUDA_TRY(cudaMemcpyAsync(dets, d_dets, nd * sizeof(pigo_det), cudaMemcpyDeviceToHost, st));  // in-place sort
   CUDA_TRY(cudaMemcpyAsync(n_out, d_nout, (size_t)nframes * 4, cudaMemcpyDeviceToHost, st));
   if (out_cap_per_frame > 0 && out)
@@ -540,6 +555,7 @@ int pigo_puploc_run(const pigo_puploc* pc, const pigo_point* seeds, int nseeds, 
   Workspace* w = g.w;
   if (!w) return set_err(PIGO_E_CUDA, "could not create a CUDA stream");
   cudaStream_t st = stream_ ? (cudaStream_t)stream_ : w->stream;
+  if ((rc = ws_enter(w, st))) return rc;
   const uint8_t* d_pix = pixels;
   if (!frames_dev) {
     const size_t bytes = (size_t)rows * dim;
@@ -575,7 +591,7 @@ int pigo_puploc_run(const pigo_puploc* pc, const pigo_point* seeds, int nseeds, 
   timing_end(T_PUPLOC, st);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
-  if (out_dev) return PIGO_OK;
+  if (out_dev) return ws_leave_async(w, st);
   CUDA_TRY(cudaMemcpyAsync(out, d_out, (size_t)nseeds * sizeof(pigo_point), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return PIGO_OK;

@@ -115,7 +115,7 @@ struct TiledArgs {
   unsigned int* tile_done_counter;        // fused kernel: tile warps that have left their tile loop
   uint32_t total_tile_warps;
   int32_t tile_warps_join_gather;         // tile warps that ran out of tiles take gather blocks
-  int32_t pad4;
+  int32_t gb_shift;                       // log2 of the gather block edge in windows (4 -> 16x16, 3 -> 8x8)
   int32_t consume_q1;                     // 0 never, 1 Q1 final at launch (gather-v2), 2 final when all tile warps are done
   int32_t gather_ni;                      // windows per lane in the gather role (ILP)
 };

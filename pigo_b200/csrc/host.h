@@ -37,6 +37,7 @@ struct Options {
   std::atomic<long long> fused_switch{0};   // tile warps join the gather role when the tiles run out
   std::atomic<long long> fused_q1{0};       // the fused kernel drains (part of) the straggler queue itself
   std::atomic<long long> tail_ctas_per_sm{0};  // grid limit (CTAs per SM) of the gather-v2 / deep tail kernels (0 = occupancy)
+  std::atomic<long long> gather_block{0};   // gather block edge in windows: 16, 8, or 0 = auto (8 for <= 4 frames)
   std::atomic<long long> deep_group{16};    // lanes (trees per step) per window in the deep kernel: 16 or 32
   std::atomic<long long> deep_smem{0};      // 1: deep kernel keeps the cascade tail in shared memory (32 warps/SM) instead of L2
   std::atomic<long long> sub_batch{32};     // frames per pipeline group (0 = whole batch)
@@ -48,7 +49,7 @@ struct Options {
     if (k == "scan_mode") scan_mode = v; else if (k == "chunk") chunk = v; else if (k == "deep_tree") deep_tree = v;
     else if (k == "gather_ctas_per_sm") gather_ctas_per_sm = v; else if (k == "tile_max_scale") tile_max_scale = v;
     else if (k == "timing") { timing = v; timing_reset(); }
-    else if (k == "gather_warps") gather_warps = v; else if (k == "gather_ks") gather_ks = v; else if (k == "deep_smem") deep_smem = v; else if (k == "deep_group") deep_group = v; else if (k == "tail_ctas_per_sm") tail_ctas_per_sm = v; else if (k == "fused_switch") fused_switch = v; else if (k == "fused_q1") fused_q1 = v; else if (k == "gather_ni") gather_ni = v; else if (k == "sub_batch") sub_batch = v; else if (k == "lanes") lanes = v;
+    else if (k == "gather_warps") gather_warps = v; else if (k == "gather_ks") gather_ks = v; else if (k == "deep_smem") deep_smem = v; else if (k == "deep_group") deep_group = v; else if (k == "gather_block") gather_block = v; else if (k == "tail_ctas_per_sm") tail_ctas_per_sm = v; else if (k == "fused_switch") fused_switch = v; else if (k == "fused_q1") fused_q1 = v; else if (k == "gather_ni") gather_ni = v; else if (k == "sub_batch") sub_batch = v; else if (k == "lanes") lanes = v;
     else if (k == "tile_warps") tile_warps = v; else if (k == "tile_ni") tile_ni = v; else if (k == "tile_ks") tile_ks = v;
     else if (k == "tile_tail_min") tile_tail_min = v; else if (k == "tile_band_ratio") tile_band_ratio = v;
     else return false;
@@ -58,7 +59,7 @@ struct Options {
     if (k == "scan_mode") return scan_mode; if (k == "chunk") return chunk; if (k == "deep_tree") return deep_tree;
     if (k == "gather_ctas_per_sm") return gather_ctas_per_sm; if (k == "tile_max_scale") return tile_max_scale;
     if (k == "timing") return timing;
-    if (k == "gather_warps") return gather_warps; if (k == "gather_ks") return gather_ks; if (k == "deep_smem") return deep_smem; if (k == "deep_group") return deep_group; if (k == "tail_ctas_per_sm") return tail_ctas_per_sm; if (k == "fused_switch") return fused_switch; if (k == "fused_q1") return fused_q1; if (k == "gather_ni") return gather_ni; if (k == "sub_batch") return sub_batch; if (k == "lanes") return lanes;
+    if (k == "gather_warps") return gather_warps; if (k == "gather_ks") return gather_ks; if (k == "deep_smem") return deep_smem; if (k == "deep_group") return deep_group; if (k == "gather_block") return gather_block; if (k == "tail_ctas_per_sm") return tail_ctas_per_sm; if (k == "fused_switch") return fused_switch; if (k == "fused_q1") return fused_q1; if (k == "gather_ni") return gather_ni; if (k == "sub_batch") return sub_batch; if (k == "lanes") return lanes;
     if (k == "tile_warps") return tile_warps; if (k == "tile_ni") return tile_ni; if (k == "tile_ks") return tile_ks;
     if (k == "tile_tail_min") return tile_tail_min; if (k == "tile_band_ratio") return tile_band_ratio;
     if (k.rfind("t_", 0) == 0) return timing_query(k);
@@ -102,6 +103,8 @@ struct Workspace {
   DevBuf deep[kMaxLanes], longq[kMaxLanes];   // Q1 / Q2 per pipeline lane
   cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t busy = nullptr;                  // last asynchronous use of this workspace (device-output calls)
+  bool busy_valid = false;
   cudaStream_t copy_stream = nullptr;          // H2D copies of host frames, one event per pipeline group
   std::vector<cudaEvent_t> copy_events;
   cudaEvent_t copy_event(int k) {
@@ -138,6 +141,7 @@ struct Workspace {
       if (ev_join[l]) cudaEventDestroy(ev_join[l]);
     }
     if (ev_fork) cudaEventDestroy(ev_fork);
+    if (busy) cudaEventDestroy(busy);
     for (auto e : copy_events) cudaEventDestroy(e);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     tiles.release(); scratch_a.release(); scratch_b.release(); scratch_c.release();

@@ -92,19 +92,21 @@ static TilePlan plan_bands(const std::vector<ScaleEntry>& plan, uint32_t tile_by
 }
 
 // Stores the prefix of 16x16-window blocks of the ladder entries [lo, hi) in ScaleEntry.pad and refreshes the device copy.
-static int upload_block_prefix(Workspace* w, int lo, int hi, cudaStream_t st, uint32_t* blocks_per_frame) {
+static int upload_block_prefix(Workspace* w, int lo, int hi, int gb_shift, cudaStream_t st, uint32_t* blocks_per_frame) {
   uint32_t nb = 0;
+  const int GB = 1 << gb_shift;
   for (int i = lo; i < hi; ++i) {
     ScaleEntry& e = w->plan_host[i];
     e.pad = nb;
-    nb += (uint32_t)((e.ncols + 15) / 16) * (uint32_t)((e.nrows + 15) / 16);
+    nb += (uint32_t)((e.ncols + GB - 1) / GB) * (uint32_t)((e.nrows + GB - 1) / GB);
   }
   *blocks_per_frame = nb;
-  if (w->pad_first_untiled != lo) {
+  const int key = lo * 8 + gb_shift;
+  if (w->pad_first_untiled != key) {
     if (cudaMemcpyAsync(w->plan.p, w->plan_host.data(), w->plan_host.size() * sizeof(ScaleEntry), cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess)
       return set_err(PIGO_E_CUDA, "plan upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-    w->pad_first_untiled = lo;
+    w->pad_first_untiled = key;
   }
   return PIGO_OK;
 }
@@ -163,6 +165,8 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
   T.gather_scale_lo = 0;
   T.gather_blocks_per_frame = 0;
   T.gather_ni = (int)std::min<long long>(std::max<long long>(1, g_opt.gather_ni.load()), 3);
+  // small batches (a frame or two) cannot fill the GPU with 256-window blocks: use 64-window blocks then
+  T.gb_shift = (g_opt.gather_block.load() == 8 || (g_opt.gather_block.load() == 0 && A.nframes <= 4)) ? 3 : 4;
 
   // ---- fused kernel: tile warps over the small scales (+ optional gather warps over the rest)
   const int ni = (int)std::min<long long>(std::max<long long>(1, g_opt.tile_ni.load()), 4);
@@ -198,7 +202,7 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
         F.tile_done_counter = (unsigned int*)(d_work + 7);
         first_untiled = tp.first_untiled;
         if (Wg > 0 && first_untiled < A.nscales) {
-          if ((rc = upload_block_prefix(w, first_untiled, A.nscales, st, &F.gather_blocks_per_frame))) return rc;
+          if ((rc = upload_block_prefix(w, first_untiled, A.nscales, T.gb_shift, st, &F.gather_blocks_per_frame))) return rc;
           F.gather_scale_lo = first_untiled;
           blocks_done = true;
         } else {
@@ -227,7 +231,7 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
     G.consume_q1 = tiled_ran ? 1 : 0;
     G.tile_warps = 0;
     if (!blocks_done && first_untiled < A.nscales) {
-      if ((rc = upload_block_prefix(w, first_untiled, A.nscales, st, &G.gather_blocks_per_frame))) return rc;
+      if ((rc = upload_block_prefix(w, first_untiled, A.nscales, T.gb_shift, st, &G.gather_blocks_per_frame))) return rc;
       G.gather_scale_lo = first_untiled;
     }
     if (G.consume_q1 || G.gather_blocks_per_frame > 0) {

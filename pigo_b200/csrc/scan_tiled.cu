@@ -156,14 +156,15 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
           }
           const ScaleEntry e = S.plan[lo];
           const uint32_t local = bidx - e.pad;
-          const uint32_t nbx = (uint32_t)(e.ncols + 15) >> 4;
+          const int gsh = A.gb_shift, GB = 1 << gsh;          // block edge in windows: 16 (default) or 8 (small batches)
+          const uint32_t nbx = (uint32_t)(e.ncols + GB - 1) >> gsh;
           const uint32_t by = local / nbx, bx = local - by * nbx;
-          b_w = min(16, e.ncols - (int)bx * 16);
-          const int b_h = min(16, e.nrows - (int)by * 16);
+          b_w = min(GB, e.ncols - (int)(bx << gsh));
+          const int b_h = min(GB, e.nrows - (int)(by << gsh));
           b_s = e.s; b_step = e.step; b_ncols = e.ncols;
-          b_r0 = e.off + (int)by * 16 * e.step;
-          b_c0 = e.off + (int)bx * 16 * e.step;
-          b_wid0 = e.wbase + by * 16u * (uint32_t)e.ncols + bx * 16u;
+          b_r0 = e.off + (int)(by << gsh) * e.step;
+          b_c0 = e.off + (int)(bx << gsh) * e.step;
+          b_wid0 = e.wbase + (by << gsh) * (uint32_t)e.ncols + (bx << gsh);
           cur = 0; end = (uint32_t)(b_w * b_h);
           continue;
         }
@@ -181,7 +182,7 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
             pc[u] = S.frames + (size_t)it.frame * S.frame_stride + (size_t)(e.off + (int)ri * e.step) * S.dim + (e.off + (int)ci * e.step);
             tbo[u] = casc + (uint32_t)it.tree * kTreeRec; acc[u] = it.acc;
           } else {
-            const uint32_t ly = b_w == 16 ? (k >> 4) : k / (uint32_t)b_w;
+            const uint32_t ly = b_w == (1 << A.gb_shift) ? (k >> A.gb_shift) : k / (uint32_t)b_w;
             const uint32_t lx = k - ly * (uint32_t)b_w;
             const int r = b_r0 + (int)ly * b_step, c = b_c0 + (int)lx * b_step;
             wid[u] = b_wid0 + ly * (uint32_t)b_ncols + lx;

@@ -254,6 +254,8 @@ VARIANTS = [
     {"scan_mode": 0, "gather_ni": 3, "sub_batch": 1, "lanes": 3, "deep_smem": 1},
     {"scan_mode": 0, "deep_group": 32, "tile_ks": 8, "gather_ks": 8, "fused_switch": 1, "fused_q1": 1},
     {"scan_mode": 0, "fused_switch": 1, "fused_q1": 0, "tile_tail_min": 33},
+    {"scan_mode": 0, "gather_block": 8},
+    {"scan_mode": 3, "gather_block": 16, "gather_ni": 2},
     {"scan_mode": 3, "gather_ks": 4},                                                   # nearly everything through the deep kernel
     {"scan_mode": 0, "gather_ks": 468, "tile_ks": 468, "tile_warps": 4, "gather_warps": 0},   # whole cascade resident: no Q2
 ]
@@ -262,7 +264,7 @@ VARIANTS = [
 @pytest.fixture
 def restore_options():
     keys = ["scan_mode", "tile_ni", "tile_warps", "tile_ks", "tile_tail_min", "tile_band_ratio", "tile_max_scale", "chunk",
-            "gather_warps", "gather_ks", "gather_ni", "sub_batch", "lanes", "deep_smem", "deep_group", "fused_switch", "fused_q1"]
+            "gather_warps", "gather_ks", "gather_ni", "sub_batch", "lanes", "deep_smem", "deep_group", "fused_switch", "fused_q1", "gather_block"]
     saved = {k: pigo_b200.get_option(k) for k in keys}
     yield
     for k, v in saved.items():
@@ -358,3 +360,49 @@ def test_rgb_to_grayscale_matches_oracle():
         assert g.shape == shape and g.dtype == np.uint8
         assert np.array_equal(g, O.rgba_to_gray(rgba))
     assert pigo_b200.RgbToGrayscale(np.zeros((0, 0, 4), np.uint8)).size == 0
+
+
+def test_concurrent_calls_on_one_classifier(gpu_face, oracle_face):
+    """The reference's methods are re-entrant on a shared classifier (read-only tables, pooled scratch); so is the C-ABI:
+    several OS threads call RunCascade on the same handle at once (ctypes releases the GIL during the call)."""
+    import threading
+    frames = synth.make_batch(6, 480, 640, "SFU", seed0=77)
+    expect = [oracle_face.run_cascade(frames[i], 480, 640, 640, *TEST_PARAMS, 0.0) for i in range(6)]
+    errors = []
+
+    def work(i):
+        try:
+            for _ in range(5):
+                g = gpu_face.run_cascade_array(cp_of(frames[i], 480, 640, 640, TEST_PARAMS), 0.0)
+                if g.tobytes() != expect[i].tobytes():
+                    errors.append(i)
+        except Exception as e:   # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert errors == []
+
+
+def test_device_resident_async_api_matches_host_api(gpu_face, oracle_face):
+    """pigo_run_cascade_batch with PIGO_FRAMES_DEVICE|PIGO_OUT_DEVICE on a caller stream (what bench.py times)."""
+    import torch
+    frames = synth.make_batch(5, 540, 960, "FSU", seed0=5)
+    d = torch.from_numpy(frames).cuda()
+    cap = 256
+    out = torch.zeros((5, cap, 4), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(5, dtype=torch.int32, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(2):   # back-to-back asynchronous calls reuse the same workspace
+            gpu_face.run_cascade_batch_device(d.data_ptr(), 5, 540 * 960, 540, 960, 960, *TEST_PARAMS, 0.0, out.data_ptr(), cap,
+                                              cnt.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    o = out.cpu().numpy().view(np.uint8).reshape(5, cap, 16)
+    for f in range(5):
+        e = oracle_face.run_cascade(frames[f], 540, 960, 960, *TEST_PARAMS, 0.0)
+        assert int(cnt[f]) == len(e)
+        assert o[f, :len(e)].tobytes() == e.tobytes()
