@@ -81,6 +81,10 @@ struct ScanArgs {
 
 // ---- tiled kernel -------------------------------------------------------------------------------------------
 constexpr int kTiledMaxThreads = 1024;
+// Tree record of the shared-memory table: 256 B node codes (node idx at byte 4*idx) | 64 f32 leaves | f32 threshold |
+// 4 B pad = 520 B.  8-byte multiple so that the two children of a node (bytes 8*idx..8*idx+7, codes or -- for the last
+// level -- leaves) can be fetched with one aligned 64-bit load; 130 words skew consecutive trees by two banks.
+constexpr int kTreeRec = 520;
 constexpr int kMaxBands = 4;
 
 // A band = consecutive ladder entries [scale_lo, scale_lo+nscales) served by one family of pixel tiles.
@@ -97,7 +101,7 @@ struct TileBand {
 
 struct TiledArgs {
   ScanArgs scan;
-  const uint8_t* tab_tiled;    // [ntrees] records of 516 bytes: 256 codes (node idx at byte 4*idx), 64 f32 leaves, f32 threshold
+  const uint8_t* tab_tiled;    // [ntrees] records of kTreeRec bytes
   int32_t ks;                  // trees resident in shared memory
   uint32_t tile_bytes;         // per-warp tile buffer
   int32_t nbands;
@@ -112,11 +116,9 @@ struct TiledArgs {
   uint32_t gather_blocks_per_frame;       // 16x16-window blocks of those scales (ScaleEntry.pad = block prefix)
   unsigned long long* gather_counter;
   unsigned long long* q1_counter;         // consumer cursor of Q1 (gather-v2 kernel only)
-  unsigned int* tile_done_counter;        // fused kernel: tile warps that have left their tile loop
-  uint32_t total_tile_warps;
-  int32_t tile_warps_join_gather;         // tile warps that ran out of tiles take gather blocks
   int32_t gb_shift;                       // log2 of the gather block edge in windows (4 -> 16x16, 3 -> 8x8)
-  int32_t consume_q1;                     // 0 never, 1 Q1 final at launch (gather-v2), 2 final when all tile warps are done
+  int32_t pad5;
+  int32_t consume_q1;                     // gather-v2 only: drain the straggler queue Q1 (complete at launch)
   int32_t gather_ni;                      // windows per lane in the gather role (ILP)
 };
 

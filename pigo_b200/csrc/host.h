@@ -34,12 +34,9 @@ struct Options {
   std::atomic<long long> tile_ks{48};       // cascade trees resident in shared memory (fused kernel)
   std::atomic<long long> gather_ks{32};     // cascade trees resident in shared memory (gather-v2 kernel)
   std::atomic<long long> gather_ni{1};      // windows per lane in the gather role / gather-v2 kernel
-  std::atomic<long long> fused_switch{0};   // tile warps join the gather role when the tiles run out
-  std::atomic<long long> fused_q1{0};       // the fused kernel drains (part of) the straggler queue itself
-  std::atomic<long long> tail_ctas_per_sm{0};  // grid limit (CTAs per SM) of the gather-v2 / deep tail kernels (0 = occupancy)
+  std::atomic<long long> fused_smem_kb{0};  // cap on the fused kernel's shared memory (0 = all 227 KB)
   std::atomic<long long> gather_block{0};   // gather block edge in windows: 16, 8, or 0 = auto (8 for <= 4 frames)
   std::atomic<long long> deep_group{16};    // lanes (trees per step) per window in the deep kernel: 16 or 32
-  std::atomic<long long> deep_smem{0};      // 1: deep kernel keeps the cascade tail in shared memory (32 warps/SM) instead of L2
   std::atomic<long long> sub_batch{32};     // frames per pipeline group (0 = whole batch)
   std::atomic<long long> lanes{1};          // internal streams the groups alternate between      // deep kernel keeps the cascade tail in shared memory when it fits
   std::atomic<long long> tile_tail_min{8};  // tail policy threshold
@@ -49,7 +46,7 @@ struct Options {
     if (k == "scan_mode") scan_mode = v; else if (k == "chunk") chunk = v; else if (k == "deep_tree") deep_tree = v;
     else if (k == "gather_ctas_per_sm") gather_ctas_per_sm = v; else if (k == "tile_max_scale") tile_max_scale = v;
     else if (k == "timing") { timing = v; timing_reset(); }
-    else if (k == "gather_warps") gather_warps = v; else if (k == "gather_ks") gather_ks = v; else if (k == "deep_smem") deep_smem = v; else if (k == "deep_group") deep_group = v; else if (k == "gather_block") gather_block = v; else if (k == "tail_ctas_per_sm") tail_ctas_per_sm = v; else if (k == "fused_switch") fused_switch = v; else if (k == "fused_q1") fused_q1 = v; else if (k == "gather_ni") gather_ni = v; else if (k == "sub_batch") sub_batch = v; else if (k == "lanes") lanes = v;
+    else if (k == "gather_warps") gather_warps = v; else if (k == "gather_ks") gather_ks = v; else if (k == "deep_group") deep_group = v; else if (k == "gather_block") gather_block = v; else if (k == "fused_smem_kb") fused_smem_kb = v; else if (k == "gather_ni") gather_ni = v; else if (k == "sub_batch") sub_batch = v; else if (k == "lanes") lanes = v;
     else if (k == "tile_warps") tile_warps = v; else if (k == "tile_ni") tile_ni = v; else if (k == "tile_ks") tile_ks = v;
     else if (k == "tile_tail_min") tile_tail_min = v; else if (k == "tile_band_ratio") tile_band_ratio = v;
     else return false;
@@ -59,7 +56,7 @@ struct Options {
     if (k == "scan_mode") return scan_mode; if (k == "chunk") return chunk; if (k == "deep_tree") return deep_tree;
     if (k == "gather_ctas_per_sm") return gather_ctas_per_sm; if (k == "tile_max_scale") return tile_max_scale;
     if (k == "timing") return timing;
-    if (k == "gather_warps") return gather_warps; if (k == "gather_ks") return gather_ks; if (k == "deep_smem") return deep_smem; if (k == "deep_group") return deep_group; if (k == "gather_block") return gather_block; if (k == "tail_ctas_per_sm") return tail_ctas_per_sm; if (k == "fused_switch") return fused_switch; if (k == "fused_q1") return fused_q1; if (k == "gather_ni") return gather_ni; if (k == "sub_batch") return sub_batch; if (k == "lanes") return lanes;
+    if (k == "gather_warps") return gather_warps; if (k == "gather_ks") return gather_ks; if (k == "deep_group") return deep_group; if (k == "gather_block") return gather_block; if (k == "fused_smem_kb") return fused_smem_kb; if (k == "gather_ni") return gather_ni; if (k == "sub_batch") return sub_batch; if (k == "lanes") return lanes;
     if (k == "tile_warps") return tile_warps; if (k == "tile_ni") return tile_ni; if (k == "tile_ks") return tile_ks;
     if (k == "tile_tail_min") return tile_tail_min; if (k == "tile_band_ratio") return tile_band_ratio;
     if (k.rfind("t_", 0) == 0) return timing_query(k);
@@ -199,7 +196,6 @@ void launch_gray(const uint8_t* rgba, size_t npix, uint8_t* gray, int grid, cuda
 void launch_scan_gather2(const TiledArgs& A, int grid, size_t smem, cudaStream_t st);
 int gather2_ctas_per_sm(size_t smem, int ng);
 void launch_deep(const ScanArgs& A, unsigned long long* counter, int grid, int group, cudaStream_t st);
-void launch_deep_smem(const ScanArgs& A, unsigned long long* counter, const uint8_t* tab_tiled, int kd, int grid, cudaStream_t st);
 int gather_max_ctas_per_sm(int depth, bool rot);
 void launch_finalize(const RawDet* raw, const int32_t* raw_count, int cap, const ScaleEntry* plan, int nscales, pigo_det* out,
                      int32_t* n_out, int nframes, cudaStream_t st);

@@ -18,11 +18,11 @@ int build_tiled_tables(const FaceTables& tab, const std::vector<int8_t>& codes, 
                        const std::vector<float>& thr, DevBuf& out) {
   if (tab.depth != 6) return PIGO_OK;  // other depths use the gather kernel only
   const size_t n = (size_t)tab.ntrees;
-  std::vector<uint8_t> rec(n * 516 + 64, 0);   // 64 spare bytes: the prefix copy is rounded up to 16 bytes
+  std::vector<uint8_t> rec(n * kTreeRec + 64, 0);   // 64 spare bytes: the prefix copy is rounded up to 16 bytes
   for (size_t t = 0; t < n; ++t) {
-    memcpy(rec.data() + t * 516, codes.data() + t * 256, 256);
-    memcpy(rec.data() + t * 516 + 256, preds.data() + t * 64, 256);
-    memcpy(rec.data() + t * 516 + 512, thr.data() + t, 4);
+    memcpy(rec.data() + t * kTreeRec, codes.data() + t * 256, 256);
+    memcpy(rec.data() + t * kTreeRec + 256, preds.data() + t * 64, 256);
+    memcpy(rec.data() + t * kTreeRec + 512, thr.data() + t, 4);
   }
   int rc = out.reserve(rec.size());
   if (rc) return rc;
@@ -160,8 +160,6 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
   T.tab_tiled = (const uint8_t*)c->tiled_tab.p;
   T.gather_counter = d_work;
   T.q1_counter = d_work + 2;
-  T.tile_done_counter = (unsigned int*)(d_work + 7);
-  T.total_tile_warps = 0;
   T.gather_scale_lo = 0;
   T.gather_blocks_per_frame = 0;
   T.gather_ni = (int)std::min<long long>(std::max<long long>(1, g_opt.gather_ni.load()), 3);
@@ -174,18 +172,21 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
   const int W = (int)std::min<long long>(std::max<long long>(0, g_opt.tile_warps.load()), max_warps);
   int Wg = (int)std::min<long long>(std::max<long long>(0, g_opt.gather_warps.load()), max_warps - W);
   auto round_ks = [&](long long v) {
-    const long long fit = (long long)((kSmemPerCta - 512) / 516);   // what one CTA's shared memory can hold at most
+    const long long fit = (long long)((kSmemPerCta - 512) / kTreeRec);   // what one CTA's shared memory can hold at most
     return (int)std::min<long long>(std::min<long long>(std::max<long long>(1, v), A.tab.ntrees), fit);
   };
   int first_untiled = 0;
-  int min_handover_tree = A.tab.ntrees;
   bool blocks_done = false, tiled_ran = false;
   if (W > 0 && mode != 3) {
     const int ks = round_ks(g_opt.tile_ks.load());
-    const size_t casc_bytes = ((size_t)ks * 516 + 15) & ~(size_t)15;   // TMA bulk copies move multiples of 16 bytes
+    const size_t casc_bytes = ((size_t)ks * kTreeRec + 15) & ~(size_t)15;   // TMA bulk copies move multiples of 16 bytes
     const size_t tiles0 = (384 + casc_bytes + 127) & ~(size_t)127;
     if (tiles0 + 4096 * (size_t)W < kSmemPerCta) {
-      const uint32_t tile_bytes = (uint32_t)(((kSmemPerCta - tiles0) / W) & ~(size_t)127);
+      // fused_smem_kb < 227 leaves the rest of the SM's 256 KB to L1 (what the gather warps' soft tiles live in)
+      size_t smem_cap = kSmemPerCta;
+      const long long lim_kb = g_opt.fused_smem_kb.load();
+      if (lim_kb > 0) smem_cap = std::min<size_t>(kSmemPerCta, std::max<size_t>((size_t)lim_kb * 1024, tiles0 + 4096 * (size_t)W));
+      const uint32_t tile_bytes = (uint32_t)(((smem_cap - tiles0) / W) & ~(size_t)127);
       int max_scale = (int)g_opt.tile_max_scale.load();
       if (max_scale <= 0) max_scale = 1 << 30;
       const TilePlan tp = plan_bands(w->plan_host, tile_bytes, max_scale, (int)std::max<long long>(100, g_opt.tile_band_ratio.load()));
@@ -197,9 +198,7 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
         F.tiles_per_frame = tp.tiles_per_frame;
         F.total_tiles = (unsigned long long)tp.tiles_per_frame * A.nframes;
         F.tile_warps = W;
-        F.consume_q1 = g_opt.fused_q1.load() ? 2 : 0;
-        F.tile_warps_join_gather = g_opt.fused_switch.load() ? 1 : 0;
-        F.tile_done_counter = (unsigned int*)(d_work + 7);
+        F.consume_q1 = 0;
         first_untiled = tp.first_untiled;
         if (Wg > 0 && first_untiled < A.nscales) {
           if ((rc = upload_block_prefix(w, first_untiled, A.nscales, T.gb_shift, st, &F.gather_blocks_per_frame))) return rc;
@@ -212,14 +211,12 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
         long long grid = num_sms;
         if (Wg == 0) grid = std::max<long long>(1, std::min<long long>(num_sms, (long long)((F.total_tiles + W - 1) / W)));
         const size_t smem = tiles0 + (size_t)tile_bytes * W;
-        F.total_tile_warps = (uint32_t)grid * (uint32_t)W;
         timing_begin(T_TILED, st);
         launch_scan_tiled(F, (int)grid, (W + Wg) * 32, smem, ni, st);
         timing_end(T_TILED, st);
         g_launches++;
         if ((rc = check_launch("fused scan"))) return rc;
         tiled_ran = true;
-        min_handover_tree = std::min(min_handover_tree, ks);
       }
     }
   }
@@ -235,13 +232,10 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
       G.gather_scale_lo = first_untiled;
     }
     if (G.consume_q1 || G.gather_blocks_per_frame > 0) {
-      min_handover_tree = std::min(min_handover_tree, G.ks);
-      const size_t smem = ((384 + (size_t)G.ks * 516 + 127) & ~(size_t)127);
+      const size_t smem = ((384 + (size_t)G.ks * kTreeRec + 127) & ~(size_t)127);
       int per_sm = (int)g_opt.gather_ctas_per_sm.load();
       const int occ = gather2_ctas_per_sm(smem, G.gather_ni);
       if (per_sm <= 0 || per_sm > occ) per_sm = occ;
-      const int tail_lim = (int)g_opt.tail_ctas_per_sm.load();
-      if (tail_lim > 0) per_sm = std::min(per_sm, tail_lim);
       timing_begin(T_GATHER, st);
       launch_scan_gather2(G, num_sms * per_sm, smem, st);
       timing_end(T_GATHER, st);
@@ -252,15 +246,8 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
 
   // ---- deep kernel: Q2, one warp per window, 32 trees per step
   {
-    // smallest tree index an item in Q2 can carry: the resident prefix of whichever kernel handed it over
-    int kd = min_handover_tree & ~3;   // 16-byte aligned start of the copied table tail
-    const size_t tail_bytes = (size_t)(A.tab.ntrees - kd) * 516 + 16;
     timing_begin(T_DEEP, st);
-    if (g_opt.deep_smem.load() && tail_bytes + 128 <= kSmemPerCta) launch_deep_smem(A, d_work + 3, (const uint8_t*)c->tiled_tab.p, kd, num_sms, st);
-    else {
-      const int tail_lim = (int)g_opt.tail_ctas_per_sm.load();
-      launch_deep(A, d_work + 3, num_sms * (tail_lim > 0 ? std::min(8, tail_lim) : 8), (int)g_opt.deep_group.load(), st);
-    }
+    launch_deep(A, d_work + 3, num_sms * 8, (int)g_opt.deep_group.load(), st);
     timing_end(T_DEEP, st);
     g_launches++;
     if ((rc = check_launch("deep scan"))) return rc;

@@ -15,35 +15,46 @@
 
 namespace pigo {
 
+// Both walks use the child-pair prefetch: the two children of node idx are adjacent (codes at bytes 8*idx.., leaves at
+// floats 2*idx-L..), so one 64-bit load fetches both while the pixel gathers of the current level are in flight and a
+// select picks the child afterwards -- one dependent L2 round trip per level instead of two.  They return the LEAF VALUE.
 template <int DEPTH>  // DEPTH = 0: runtime depth
-__device__ __forceinline__ int walk_tree(const int8_t* __restrict__ tc, const uint8_t* __restrict__ pc, int s, int dim,
-                                         int depth) {
-  int idx = 1;
+__device__ __forceinline__ float walk_tree(const int8_t* __restrict__ tc, const float* __restrict__ tp, const uint8_t* __restrict__ pc,
+                                           int s, int dim, int depth, int leaves) {
   const int D = DEPTH ? DEPTH : depth;
+  const int2* tc2 = reinterpret_cast<const int2*>(tc);
+  const int2* tp2 = reinterpret_cast<const int2*>(tp);
+  int idx = 1;
+  int cw = __ldg(reinterpret_cast<const int*>(tc) + 1);
 #pragma unroll
   for (int j = 0; j < D; ++j) {
-    const int cw = __ldg(reinterpret_cast<const int*>(tc) + idx);
+    const int2 kids = (j < D - 1) ? __ldg(tc2 + idx) : __ldg(tp2 + (idx - (leaves >> 1)));
     // ((r*256 + code*s) >> 8) == r + ((code*s) >> 8): r*256 is a multiple of 256 (core/pigo.go:126-127)
     const int o1 = (((int)(int8_t)(cw) * s) >> 8) * dim + (((int)(int8_t)(cw >> 8) * s) >> 8);
     const int o2 = (((int)(int8_t)(cw >> 16) * s) >> 8) * dim + (((cw >> 24) * s) >> 8);
     const unsigned p1 = __ldg(pc + o1), p2 = __ldg(pc + o2);
-    idx = 2 * idx + (p1 <= p2 ? 1 : 0);  // core/pigo.go:129-135
+    const bool right = p1 <= p2;           // core/pigo.go:129-135
+    cw = right ? kids.y : kids.x;
+    idx = 2 * idx + (right ? 1 : 0);
   }
-  return idx;
+  return __int_as_float(cw);
 }
 
 // classifyRotatedRegion node walk (core/pigo.go:164-180).  NB: both coordinates are clamped with
 // nrows-1 (:167-171) -- reproduced on purpose.  64-bit intermediates like Go's int.
 template <int DEPTH>
-__device__ __forceinline__ int walk_tree_rot(const int8_t* __restrict__ tc, const uint8_t* __restrict__ frame, int r, int c,
-                                             long long qsin, long long qcos, int nrows, int dim, int depth) {
-  int idx = 1;
+__device__ __forceinline__ float walk_tree_rot(const int8_t* __restrict__ tc, const float* __restrict__ tp, const uint8_t* __restrict__ frame,
+                                               int r, int c, long long qsin, long long qcos, int nrows, int dim, int depth, int leaves) {
   const int D = DEPTH ? DEPTH : depth;
   const long long lim = nrows - 1;
   const long long r16 = 65536ll * r, c16 = 65536ll * c;
+  const int2* tc2 = reinterpret_cast<const int2*>(tc);
+  const int2* tp2 = reinterpret_cast<const int2*>(tp);
+  int idx = 1;
+  int cw = __ldg(reinterpret_cast<const int*>(tc) + 1);
 #pragma unroll
   for (int j = 0; j < D; ++j) {
-    const int cw = __ldg(reinterpret_cast<const int*>(tc) + idx);
+    const int2 kids = (j < D - 1) ? __ldg(tc2 + idx) : __ldg(tp2 + (idx - (leaves >> 1)));
     const long long k0 = (int8_t)(cw), k1 = (int8_t)(cw >> 8), k2 = (int8_t)(cw >> 16), k3 = (cw >> 24);
     long long r1 = min(lim, max(0ll, r16 + qcos * k0 - qsin * k1) >> 16);
     long long c1 = min(lim, max(0ll, c16 + qsin * k0 + qcos * k1) >> 16);
@@ -51,9 +62,11 @@ __device__ __forceinline__ int walk_tree_rot(const int8_t* __restrict__ tc, cons
     long long c2 = min(lim, max(0ll, c16 + qsin * k2 + qcos * k3) >> 16);
     r1 = r1 < 0 ? -r1 : r1; c1 = c1 < 0 ? -c1 : c1; r2 = r2 < 0 ? -r2 : r2; c2 = c2 < 0 ? -c2 : c2;  // abs(), :167
     const unsigned p1 = __ldg(frame + r1 * dim + c1), p2 = __ldg(frame + r2 * dim + c2);
-    idx = 2 * idx + (p1 <= p2 ? 1 : 0);
+    const bool right = p1 <= p2;
+    cw = right ? kids.y : kids.x;
+    idx = 2 * idx + (right ? 1 : 0);
   }
-  return idx;
+  return __int_as_float(cw);
 }
 
 template <int DEPTH, bool ROT>
@@ -120,15 +133,16 @@ __global__ void __launch_bounds__(256) scan_gather_kernel(const ScanArgs A) {
     if (!__any_sync(FULL, alive)) break;
     if (alive) {
       const int8_t* tc = T.codes + (size_t)t * code_stride;
-      int idx;
+      const float* tp = T.preds + (size_t)t * L;
+      float pred;
       if (ROT) {
         const long long qsin = (long long)s * c_qsin[A.rot_slot];  // core/pigo.go:159
         const long long qcos = (long long)s * c_qcos[A.rot_slot];  // :160
-        idx = walk_tree_rot<DEPTH>(tc, pc, r, c, qsin, qcos, A.rows, A.dim, T.depth);
+        pred = walk_tree_rot<DEPTH>(tc, tp, pc, r, c, qsin, qcos, A.rows, A.dim, T.depth, L);
       } else {
-        idx = walk_tree<DEPTH>(tc, pc, s, A.dim, T.depth);
+        pred = walk_tree<DEPTH>(tc, tp, pc, s, A.dim, T.depth, L);
       }
-      acc += __ldg(T.preds + (size_t)t * L + idx - L);  // core/pigo.go:137 (float32, tree order)
+      acc += pred;                                       // core/pigo.go:137 (float32, tree order)
       const float thr = __ldg(T.thresh + t);
       if (acc <= thr) {                                  // :139-141
         alive = false;

@@ -2,7 +2,7 @@
 // (core/pigo.go:113-147): the warp-specialised FUSED kernel (tile warps + gather warps) and the gather-v2 kernel.
 //
 //  * Fused kernel: persistent CTA (one per SM).  The first KS trees of the cascade (codes, leaves, threshold: one
-//    516-byte record per tree, 129 words so consecutive trees are skewed by one bank) are staged ONCE per CTA into
+//    520-byte record per tree, see kTreeRec) are staged ONCE per CTA into
 //    shared memory by the TMA bulk engine (cp.async.bulk + mbarrier).
 //  * TILE WARPS, one warp per image tile: each warp owns a private pixel-tile buffer in shared memory.  A tile is an
 //    image region (core + halo) that serves EVERY scale of a band (20..39 px) at once, so the frame is read from
@@ -54,9 +54,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 constexpr uint32_t kCascOff = 384;  // mbarriers live in the first 384 bytes of shared memory
-constexpr int kTreeRec = 516;  // bytes per tree record in the tiled table: 256 codes + 256 leaves + 4 threshold (depth 6)
-
 __device__ __forceinline__ int ceil_div_pos(int num, int den) { return num <= 0 ? 0 : (num + den - 1) / den; }
+
+
 
 // sign-extended byte k of a packed code word: one PRMT (selector nibble with bit 3 set replicates the sign)
 // (prmt.b32 default mode; __byte_perm() documents only 3 selector bits, so the PTX instruction is spelled out)
@@ -77,15 +77,11 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
   const ScanArgs& S = A.scan;
   const FaceTables T = S.tab;
   const unsigned long long total_blocks = (unsigned long long)A.gather_blocks_per_frame * S.nframes;
-  // consume_q1: 0 = never, 1 = Q1 is complete when this kernel starts (gather-v2), 2 = fused kernel: Q1 becomes
-  // readable once EVERY tile warp of the grid has left its tile loop (tile_done_counter == total_tile_warps)
-  uint32_t q1n = A.consume_q1 == 1 ? min(*S.deep_count, S.deep_cap) : 0u;
-  bool q1_more = q1n > 0, blocks_more = total_blocks > 0, q1_late_checked = A.consume_q1 != 2;
+  // Q1 (stragglers of the tile warps) is complete when the gather-v2 kernel starts; the fused kernel never reads it
+  const uint32_t q1n = A.consume_q1 ? min(*S.deep_count, S.deep_cap) : 0u;
+  bool q1_more = q1n > 0, blocks_more = total_blocks > 0;
   bool from_q1 = false;
-  // In the fused kernel a warp drains at most a few chunks: whoever arrives last must not serialise the whole queue
-  // on one warp -- what is left is picked up by the full-grid gather-v2 launch that follows.
-  int q1_budget = A.consume_q1 == 2 ? 4 : 0x7fffffff;
-  if (!blocks_more && !q1_more && q1_late_checked) return;
+  if (!blocks_more && !q1_more) return;
   const uint32_t tbo_last = casc + (uint32_t)T.ntrees * kTreeRec;   // record offset "one past the last tree"
 
   // NG independent windows per lane: their dependent LDS -> L2 gather chains overlap (ILP), which is what hides the
@@ -111,7 +107,6 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
       while (need && more) {
         if (cur == end) {
           unsigned long long g = 0;
-          if (q1_more && q1_budget-- <= 0) q1_more = false;
           if (q1_more) {                       // stragglers: 32 queue items per grab
             if (lane == 0) g = atomicAdd(A.q1_counter, 1ull);
             g = __shfl_sync(FULL, g, 0);
@@ -129,21 +124,6 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
             if (g >= total_blocks) blocks_more = false;
           }
           if (!blocks_more) {
-            if (!q1_late_checked) {
-              // fused kernel, out of blocks: if every tile warp has finished, the straggler queue is final -- drain it
-              q1_late_checked = true;
-              unsigned done = 0;
-              if (lane == 0) done = atomicAdd(A.tile_done_counter, 0u);
-              done = __shfl_sync(FULL, done, 0);
-              if (done == A.total_tile_warps) {
-                __threadfence();
-                unsigned n = 0;
-                if (lane == 0) n = atomicAdd(S.deep_count, 0u);
-                q1n = min(__shfl_sync(FULL, n, 0), S.deep_cap);
-                q1_more = q1n > 0;
-                if (q1_more) continue;
-              }
-            }
             more = false;
             break;
           }
@@ -209,13 +189,14 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
     int idx[NG];
     float pred[NG], thr[NG];
     if (!__any_sync(FULL, beyond)) {
+      int cw[NG];
 #pragma unroll
-      for (int u = 0; u < NG; ++u) idx[u] = 1;
+      for (int u = 0; u < NG; ++u) { idx[u] = 1; cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4); }
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
-        int cw[NG];
+        int2 kids[NG];   // child-pair prefetch (see the tile role): one 64-bit shared load beside the two pixel gathers
 #pragma unroll
-        for (int u = 0; u < NG; ++u) cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4 * idx[u]);
+        for (int u = 0; u < NG; ++u) kids[u] = *reinterpret_cast<const int2*>(smem + tbo[u] + 8 * idx[u]);
         unsigned p1[NG], p2[NG];
 #pragma unroll
         for (int u = 0; u < NG; ++u) {
@@ -226,11 +207,15 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
           p2[u] = __ldg(pc[u] + o2);
         }
 #pragma unroll
-        for (int u = 0; u < NG; ++u) idx[u] = 2 * idx[u] + (p1[u] <= p2[u] ? 1 : 0);
+        for (int u = 0; u < NG; ++u) {
+          const bool right = p1[u] <= p2[u];
+          cw[u] = right ? kids[u].y : kids[u].x;
+          idx[u] = 2 * idx[u] + (right ? 1 : 0);
+        }
       }
 #pragma unroll
       for (int u = 0; u < NG; ++u) {
-        pred[u] = *reinterpret_cast<const float*>(smem + tbo[u] + 4 * idx[u]);
+        pred[u] = __int_as_float(cw[u]);
         thr[u] = *reinterpret_cast<const float*>(smem + tbo[u] + 512);
       }
     } else {
@@ -492,14 +477,18 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
 
       // ================= one tree per live item =================================================================
       if (!overflow_mode) {
-        int idx[NI];
+        // Child-pair prefetch: the two children of node idx sit at bytes 8*idx .. 8*idx+7 of the record (codes, or the
+        // two leaves after the last level), so they are fetched with ONE 64-bit load issued together with the pixel
+        // gathers of the current level; after the comparison a select picks the child.  That takes the node-code load
+        // off the dependent chain of every level (and the leaf load off its end).
+        int idx[NI], cw[NI];
 #pragma unroll
-        for (int u = 0; u < NI; ++u) idx[u] = 1;
+        for (int u = 0; u < NI; ++u) { idx[u] = 1; cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4); }
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-          int cw[NI];
+          int2 kids[NI];
 #pragma unroll
-          for (int u = 0; u < NI; ++u) cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4 * idx[u]);
+          for (int u = 0; u < NI; ++u) kids[u] = *reinterpret_cast<const int2*>(smem + tbo[u] + 8 * idx[u]);
           uint32_t p1[NI], p2[NI];
 #pragma unroll
           for (int u = 0; u < NI; ++u) {
@@ -511,13 +500,17 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
             p2[u] = smem[pb[u] + o2];
           }
 #pragma unroll
-          for (int u = 0; u < NI; ++u) idx[u] = 2 * idx[u] + (p1[u] <= p2[u] ? 1 : 0);   // core/pigo.go:129-135
+          for (int u = 0; u < NI; ++u) {
+            const bool right = p1[u] <= p2[u];                                  // core/pigo.go:129-135
+            cw[u] = right ? kids[u].y : kids[u].x;
+            idx[u] = 2 * idx[u] + (right ? 1 : 0);
+          }
         }
         bool hit = false;
         float thr_last[NI];
 #pragma unroll
         for (int u = 0; u < NI; ++u) {
-          const float pred = *reinterpret_cast<const float*>(smem + tbo[u] + 4 * idx[u]);  // leaves at words 64..127
+          const float pred = __int_as_float(cw[u]);         // after the last level the selected "child" is the leaf value
           const float thr = *reinterpret_cast<const float*>(smem + tbo[u] + 512);
           thr_last[u] = thr;
           acc[u] += pred;                                   // core/pigo.go:137 (float32, tree order)
@@ -596,16 +589,6 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
       }
     }
   }
-
-  // ---- out of tiles: announce it (the straggler queue is final once every tile warp has), then help the gather role
-  __syncwarp();
-  if (lane == 0) {
-    __threadfence();
-    atomicAdd(A.tile_done_counter, 1u);
-  }
-  if (!A.tile_warps_join_gather) return;
-  if (A.gather_ni >= 2) gather_role<2>(A, smem, casc, casc_end);
-  else gather_role<1>(A, smem, casc, casc_end);
 }
 
 template <int NI, int MAXT>

@@ -251,10 +251,12 @@ VARIANTS = [
     {"scan_mode": 0, "gather_warps": 0, "tile_warps": 8, "tile_ni": 2},               # tiles fused kernel + separate gather launch
     {"scan_mode": 0, "gather_warps": 24, "tile_warps": 8, "tile_ni": 1, "tile_ks": 32},
     {"scan_mode": 3, "gather_ks": 32, "gather_ni": 1, "sub_batch": 2, "lanes": 2},      # gather-v2 + deep kernel only
-    {"scan_mode": 0, "gather_ni": 3, "sub_batch": 1, "lanes": 3, "deep_smem": 1},
-    {"scan_mode": 0, "deep_group": 32, "tile_ks": 8, "gather_ks": 8, "fused_switch": 1, "fused_q1": 1},
-    {"scan_mode": 0, "fused_switch": 1, "fused_q1": 0, "tile_tail_min": 33},
+    {"scan_mode": 0, "gather_ni": 3, "sub_batch": 1, "lanes": 3},
+    {"scan_mode": 0, "deep_group": 32, "tile_ks": 8, "gather_ks": 8},
+    {"scan_mode": 0, "tile_tail_min": 33, "tile_ks": 5, "gather_ks": 7},
     {"scan_mode": 0, "gather_block": 8},
+    {"scan_mode": 0, "fused_smem_kb": 160, "tile_warps": 14, "gather_warps": 18},
+    {"scan_mode": 0, "tile_warps": 4, "gather_warps": 28, "tile_max_scale": 24},
     {"scan_mode": 3, "gather_block": 16, "gather_ni": 2},
     {"scan_mode": 3, "gather_ks": 4},                                                   # nearly everything through the deep kernel
     {"scan_mode": 0, "gather_ks": 468, "tile_ks": 468, "tile_warps": 4, "gather_warps": 0},   # whole cascade resident: no Q2
@@ -264,7 +266,7 @@ VARIANTS = [
 @pytest.fixture
 def restore_options():
     keys = ["scan_mode", "tile_ni", "tile_warps", "tile_ks", "tile_tail_min", "tile_band_ratio", "tile_max_scale", "chunk",
-            "gather_warps", "gather_ks", "gather_ni", "sub_batch", "lanes", "deep_smem", "deep_group", "fused_switch", "fused_q1", "gather_block"]
+            "gather_warps", "gather_ks", "gather_ni", "sub_batch", "lanes", "deep_group", "gather_block", "fused_smem_kb"]
     saved = {k: pigo_b200.get_option(k) for k in keys}
     yield
     for k, v in saved.items():
@@ -406,3 +408,32 @@ def test_device_resident_async_api_matches_host_api(gpu_face, oracle_face):
         e = oracle_face.run_cascade(frames[f], 540, 960, 960, *TEST_PARAMS, 0.0)
         assert int(cnt[f]) == len(e)
         assert o[f, :len(e)].tobytes() == e.tobytes()
+
+
+def _synthetic_cascade(depth: int, ntrees: int, seed: int) -> bytes:
+    """A random cascade in the facefinder binary layout (core/pigo.go:51-110) with thresholds loose enough to let windows through."""
+    rng = np.random.default_rng(seed)
+    L = 1 << depth
+    out = bytearray(b"\x03\x00\x00\x00\x81\x7f\x81\x7f")
+    out += np.uint32(depth).tobytes() + np.uint32(ntrees).tobytes()
+    for t in range(ntrees):
+        out += rng.integers(-128, 128, size=4 * L - 4, dtype=np.int8).tobytes()
+        out += rng.uniform(-1.0, 1.0, size=L).astype("<f4").tobytes()
+        out += np.float32(-0.6 - 0.25 * t).tobytes()
+    return bytes(out)
+
+
+@pytest.mark.parametrize("depth,ntrees", [(6, 3), (6, 70), (4, 9), (1, 2), (8, 5), (6, 1)])
+def test_synthetic_cascades_other_depths_and_sizes(depth, ntrees, restore_options):
+    """Generic tree depth (universal gather kernel) and tiny / odd-sized depth-6 cascades (resident prefix larger than the
+    cascade, Q2 never used, ...), unrotated and rotated."""
+    pk = _synthetic_cascade(depth, ntrees, seed=depth * 100 + ntrees)
+    clf = pigo_b200.NewPigo().Unpack(pk)
+    ora = O.OracleFace(pk)
+    assert (clf.treeDepth, clf.treeNum) == (depth, ntrees) == (ora.depth, ora.ntrees)
+    img = synth.frame_smooth(300, 420, seed=depth + ntrees, sigma=3.0)
+    for ang in (0.0, 0.4):
+        for prm in ((20, 200, 0.2, 1.2), (24, 60, 0.1, 1.1)):
+            g = clf.run_cascade_array(cp_of(img, 300, 420, 420, prm), ang, cap=64)
+            o = ora.run_cascade(img, 300, 420, 420, *prm, ang, cap=1 << 18)
+            assert_same(g, o)
