@@ -59,8 +59,14 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise ImportError(f"{LIB_PATH} is missing: build it with `python -m pigo_b200.build` "
-                              "(there is no CPU or PyTorch fallback for the detection path)")
+            # not built yet (fresh checkout): compile it in-tree with nvcc; there is no CPU or PyTorch fallback, so a
+            # missing toolchain is a hard error
+            try:
+                from . import build as _build
+                _build.build()
+            except Exception as e:
+                raise ImportError(f"{LIB_PATH} is missing and could not be built with nvcc ({e}); "
+                                  "there is no CPU or PyTorch fallback for the detection path") from e
         L = C.CDLL(LIB_PATH)
         vp, i, d, u64, sz = C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_size_t
         L.pigo_last_error.restype = C.c_char_p

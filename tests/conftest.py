@@ -13,6 +13,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """Build the in-tree artefacts if they are missing or stale (nvcc cross-compiles without a GPU; gcc for the oracle)."""
+    from pigo_b200 import build
+    build.build()
+    import oracle_lib
+    oracle_lib.build()
+
+
 @pytest.fixture(scope="session")
 def golden():
     import numpy as np
