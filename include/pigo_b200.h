@@ -81,6 +81,11 @@ int64_t pigo_launch_count(void);
 /* Pinned host memory for zero-staging H2D copies of frame batches. */
 int pigo_alloc_pinned(void **ptr, size_t bytes);
 int pigo_free_pinned(void *ptr);
+/* Device buffers for callers that keep a frame batch resident across several calls (RunCascade, then RunDetector /
+ * GetLandmarkPoint on the same frames) and pass it with PIGO_FRAMES_DEVICE. */
+int pigo_device_alloc(void **ptr, size_t bytes);
+int pigo_device_free(void *ptr);
+int pigo_device_upload(void *dst_device, const void *src_host, size_t bytes);
 
 /* ---- face cascade: (*Pigo).Unpack, core/pigo.go:51-110 --------------------------------- */
 /* Parses the `facefinder` binary layout (8 ignored bytes, u32 depth, u32 ntrees, then per
@@ -138,6 +143,13 @@ int pigo_puploc_info(const pigo_puploc *p, uint32_t *stages, float *scale_mul, u
 int pigo_puploc_run(const pigo_puploc *p, const pigo_point *seeds, int nseeds, const float *randoms,
                     uint64_t rng_seed, const uint8_t *pixels, int rows, int cols, int dim, double angle,
                     const uint8_t *flipv, pigo_point *out, unsigned flags, void *stream);
+
+/* Additive batch form over several frames of identical geometry: seed i refines on frame seed_frame[i]
+ * (frames `frame_stride` bytes apart; seed_frame may be NULL when nframes == 1). */
+int pigo_puploc_run_frames(const pigo_puploc *p, const pigo_point *seeds, int nseeds, const int32_t *seed_frame,
+                           const float *randoms, uint64_t rng_seed, const uint8_t *frames, int nframes,
+                           size_t frame_stride, int rows, int cols, int dim, double angle, const uint8_t *flipv,
+                           pigo_point *out, unsigned flags, void *stream);
 
 /* ---- (*PuplocCascade).GetLandmarkPoint(leftEye, rightEye *Puploc, img, perturb, flipV) *Puploc,
  * core/flploc.go:36-57: seed arithmetic in float64 on the host, then RunDetector(angle 0). */

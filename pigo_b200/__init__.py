@@ -41,7 +41,8 @@ ABI_SYMBOLS = [
     "pigo_free_pinned", "pigo_cascade_create", "pigo_cascade_destroy", "pigo_cascade_info", "pigo_scale_ladder",
     "pigo_count_windows", "pigo_run_cascade", "pigo_run_cascade_batch", "pigo_cluster", "pigo_cluster_batch",
     "pigo_puploc_create", "pigo_puploc_destroy", "pigo_puploc_info", "pigo_puploc_run", "pigo_get_landmark_point",
-    "pigo_set_option", "pigo_get_option", "pigo_rgba_to_gray",
+    "pigo_set_option", "pigo_get_option", "pigo_rgba_to_gray", "pigo_puploc_run_frames", "pigo_device_alloc",
+    "pigo_device_free", "pigo_device_upload",
 ]
 
 
@@ -92,6 +93,10 @@ def lib() -> C.CDLL:
         L.pigo_puploc_run.argtypes = [vp, vp, i, vp, u64, vp, i, i, i, d, vp, vp, C.c_uint, vp]
         L.pigo_get_landmark_point.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp, u64, vp]
         L.pigo_rgba_to_gray.argtypes = [vp, sz, vp, C.c_uint, vp]
+        L.pigo_puploc_run_frames.argtypes = [vp, vp, i, vp, vp, u64, vp, i, sz, i, i, i, d, vp, vp, C.c_uint, vp]
+        L.pigo_device_alloc.argtypes = [C.POINTER(vp), sz]
+        L.pigo_device_free.argtypes = [vp]
+        L.pigo_device_upload.argtypes = [vp, vp, sz]
         L.pigo_set_option.argtypes = [C.c_char_p, C.c_int64]
         L.pigo_get_option.argtypes = [C.c_char_p]
         L.pigo_get_option.restype = C.c_int64
@@ -233,20 +238,26 @@ class Pigo:
         """(*Pigo).RunCascade, core/pigo.go:212-258."""
         return _array_to_dets(self.run_cascade_array(cp, angle))
 
-    def RunCascadeBatch(self, frames: np.ndarray, cp: CascadeParams, angle: float = 0.0, cap_per_frame: int = 1024):
-        """Additive batch entry point: frames is (N, Rows, Dim) uint8 on the host.
+    def RunCascadeBatch(self, frames, cp: CascadeParams, angle: float = 0.0, cap_per_frame: int = 1024):
+        """Additive batch entry point: frames is (N, Rows, Dim) uint8 on the host, or a DeviceFrames.
         Returns (dets[N, cap] DET_DTYPE, counts[N])."""
         self._need()
-        frames = np.ascontiguousarray(frames, dtype=np.uint8)
-        nf = frames.shape[0]
         img = cp.ImageParams
-        stride = frames.strides[0] if nf > 0 else 0
+        on_dev = isinstance(frames, DeviceFrames)
+        if on_dev:
+            nf, stride, fptr = frames.nframes, frames.stride, frames.ptr
+        else:
+            frames = np.ascontiguousarray(frames, dtype=np.uint8)
+            nf = frames.shape[0]
+            stride = frames.strides[0] if nf > 0 else 0
+            fptr = frames.ctypes.data
         while True:
             out = np.zeros((nf, max(cap_per_frame, 1)), dtype=DET_DTYPE)
             cnt = np.zeros(max(nf, 1), dtype=np.int32)
-            rc = lib().pigo_run_cascade_batch(self._h, frames.ctypes.data, nf, stride, img.Rows, img.Cols, img.Dim,
+            rc = lib().pigo_run_cascade_batch(self._h, fptr, nf, stride, img.Rows, img.Cols, img.Dim,
                                               cp.MinSize, cp.MaxSize, cp.ShiftFactor, cp.ScaleFactor, angle,
-                                              out.ctypes.data, cap_per_frame, cnt.ctypes.data, MEM_HOST, None)
+                                              out.ctypes.data, cap_per_frame, cnt.ctypes.data,
+                                              FRAMES_DEVICE if on_dev else MEM_HOST, None)
             if rc == PIGO_E_CAP:
                 cap_per_frame = int(cnt.max())
                 continue
@@ -272,6 +283,19 @@ class Pigo:
         k = C.c_int()
         _check(lib().pigo_cluster(d.ctypes.data, n, iou, out.ctypes.data, cap, C.byref(k)))
         return d, out[:k.value].copy()
+
+    def cluster_batch_array(self, dets: np.ndarray, counts: np.ndarray, iou: float):
+        """ClusterDetections for every frame of a RunCascadeBatch result in one launch.
+        dets: [N, cap] DET_DTYPE (sorted in place per frame), counts: [N].  Returns (clusters[N, cap], nclusters[N])."""
+        d = np.ascontiguousarray(dets, dtype=DET_DTYPE)
+        nf, cap = d.shape
+        n = np.ascontiguousarray(np.minimum(counts, cap), dtype=np.int32)
+        out = np.zeros((nf, max(cap, 1)), dtype=DET_DTYPE)
+        k = np.zeros(max(nf, 1), dtype=np.int32)
+        _check(lib().pigo_cluster_batch(d.ctypes.data, n.ctypes.data, nf, cap, iou, out.ctypes.data, cap, k.ctypes.data, MEM_HOST, None))
+        if d is not dets and isinstance(dets, np.ndarray) and dets.shape == d.shape:
+            dets[...] = d
+        return out, k[:nf]
 
     def ClusterDetections(self, detections: List[Detection], iouThreshold: float) -> List[Detection]:
         """(*Pigo).ClusterDetections, core/pigo.go:262-308; sorts `detections` in place like the reference."""
@@ -351,6 +375,34 @@ class PuplocCascade:
                                      fl.ctypes.data if fl is not None else None, out.ctypes.data, MEM_HOST, None))
         return [Puploc(int(o["row"]), int(o["col"]), float(np.float32(o["scale"])), int(o["perturbs"])) for o in out[:n]]
 
+    def run_detector_frames(self, seeds: Sequence[Puploc], seed_frame: Sequence[int], frames, nframes: int, frame_stride: int,
+                            rows: int, cols: int, dim: int, angle: float = 0.0, flipv: Optional[Sequence[bool]] = None,
+                            randoms: Optional[np.ndarray] = None, rng_seed: int = 0, frames_on_device: bool = False) -> List[Puploc]:
+        """Batch over several frames: seed i refines on frame seed_frame[i].  `frames` is a host uint8 array, or a device
+        pointer (int) when frames_on_device."""
+        if self._h is None:
+            raise PigoError(PIGO_E_INVALID, "cascade not unpacked")
+        n = len(seeds)
+        if n == 0:
+            return []
+        s = np.zeros(n, dtype=POINT_DTYPE)
+        for k, p in enumerate(seeds):
+            s[k] = (p.Row, p.Col, p.Scale, p.Perturbs)
+        sf = np.ascontiguousarray(np.asarray(seed_frame, dtype=np.int32))
+        out = np.zeros(n, dtype=POINT_DTYPE)
+        rnd = np.ascontiguousarray(randoms, dtype=np.float32) if randoms is not None else None
+        fl = np.ascontiguousarray(np.asarray(flipv, dtype=np.uint8)) if flipv is not None else None
+        if frames_on_device:
+            fptr = int(frames)
+        else:
+            fr = np.ascontiguousarray(frames, dtype=np.uint8)
+            fptr = fr.ctypes.data
+        _check(lib().pigo_puploc_run_frames(self._h, s.ctypes.data, n, sf.ctypes.data, rnd.ctypes.data if rnd is not None else None,
+                                            rng_seed, fptr, nframes, frame_stride, rows, cols, dim, angle,
+                                            fl.ctypes.data if fl is not None else None, out.ctypes.data,
+                                            FRAMES_DEVICE if frames_on_device else MEM_HOST, None))
+        return [Puploc(int(o["row"]), int(o["col"]), float(np.float32(o["scale"])), int(o["perturbs"])) for o in out]
+
     def RunDetector(self, pl: Puploc, img: ImageParams, angle: float, flipV: bool, randoms: Optional[np.ndarray] = None,
                     rng_seed: int = 0) -> Puploc:
         """(*PuplocCascade).RunDetector, core/puploc.go:239-277 (randoms: optional [63][3] float32 injection)."""
@@ -408,6 +460,29 @@ def RgbToGrayscale(rgba: np.ndarray) -> np.ndarray:
     out = np.zeros(a.shape[:-1], dtype=np.uint8)
     _check(lib().pigo_rgba_to_gray(a.ctypes.data if n else None, n, out.ctypes.data if n else None, MEM_HOST, None))
     return out
+
+
+class DeviceFrames:
+    """A frame batch kept resident on the device across calls (pigo_device_alloc/_upload/_free)."""
+
+    def __init__(self, frames: np.ndarray):
+        fr = np.ascontiguousarray(frames, dtype=np.uint8)
+        self.nframes = fr.shape[0]
+        self.stride = fr.strides[0] if fr.ndim == 3 else fr.size
+        self.nbytes = fr.nbytes
+        p = C.c_void_p()
+        _check(lib().pigo_device_alloc(C.byref(p), self.nbytes))
+        self.ptr = p.value
+        _check(lib().pigo_device_upload(self.ptr, fr.ctypes.data, self.nbytes))
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            lib().pigo_device_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        if _lib is not None:
+            self.free()
 
 
 def load_cascade(name: str = "facefinder") -> bytes:

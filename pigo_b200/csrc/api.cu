@@ -190,6 +190,26 @@ int pigo_free_pinned(void* ptr) {
   return PIGO_OK;
 }
 
+int pigo_device_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return set_err(PIGO_E_INVALID, "null ptr");
+  int rc = ensure_device();
+  if (rc) return rc;
+  if (cudaMalloc(ptr, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return set_err(PIGO_E_NOMEM, "cudaMalloc(%zu) failed", bytes); }
+  return PIGO_OK;
+}
+int pigo_device_free(void* ptr) {
+  if (ptr) CUDA_TRY(cudaFree(ptr));
+  return PIGO_OK;
+}
+int pigo_device_upload(void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return PIGO_OK;
+  if (!dst || !src) return set_err(PIGO_E_INVALID, "null argument");
+  int rc = ensure_device();
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return PIGO_OK;
+}
+
 int pigo_set_option(const char* name, int64_t value) {
   if (!name) return set_err(PIGO_E_INVALID, "null option name");
   return g_opt.set(name, value) ? PIGO_OK : set_err(PIGO_E_INVALID, "unknown option '%s'", name);
@@ -540,17 +560,27 @@ int pigo_puploc_info(const pigo_puploc* p, uint32_t* stages, float* scale_mul, u
 int pigo_puploc_run(const pigo_puploc* pc, const pigo_point* seeds, int nseeds, const float* randoms, uint64_t rng_seed,
                     const uint8_t* pixels, int rows, int cols, int dim, double angle, const uint8_t* flipv, pigo_point* out,
                     unsigned flags, void* stream_) {
+  return pigo_puploc_run_frames(pc, seeds, nseeds, nullptr, randoms, rng_seed, pixels, 1, (size_t)std::max(rows, 0) * (size_t)std::max(dim, 0),
+                                rows, cols, dim, angle, flipv, out, flags, stream_);
+}
+
+int pigo_puploc_run_frames(const pigo_puploc* pc, const pigo_point* seeds, int nseeds, const int32_t* seed_frame, const float* randoms,
+                           uint64_t rng_seed, const uint8_t* pixels, int nframes, size_t frame_stride, int rows, int cols, int dim,
+                           double angle, const uint8_t* flipv, pigo_point* out, unsigned flags, void* stream_) {
   pigo_puploc* p = const_cast<pigo_puploc*>(pc);
   if (!p || !seeds || !out || !pixels) return set_err(PIGO_E_INVALID, "null argument");
-  if (nseeds < 0 || rows <= 0 || cols <= 0 || dim < cols) return set_err(PIGO_E_INVALID, "bad geometry");
+  if (nseeds < 0 || rows <= 0 || cols <= 0 || dim < cols || nframes < 1) return set_err(PIGO_E_INVALID, "bad geometry");
+  if (nframes > 1 && !seed_frame) return set_err(PIGO_E_INVALID, "seed_frame is required when nframes > 1");
   int rc = ensure_device();
   if (rc) return rc;
   if (nseeds == 0) return PIGO_OK;
   const bool frames_dev = flags & PIGO_FRAMES_DEVICE, out_dev = flags & PIGO_OUT_DEVICE;
   if (!out_dev)
-    for (int i = 0; i < nseeds; ++i)
+    for (int i = 0; i < nseeds; ++i) {
       if (seeds[i].perturbs < 0 || seeds[i].perturbs > 63)
         return set_err(PIGO_E_INVALID, "seed %d: Perturbs=%d outside 0..63 (the reference panics, core/puploc.go:261)", i, seeds[i].perturbs);
+      if (seed_frame && (seed_frame[i] < 0 || seed_frame[i] >= nframes)) return set_err(PIGO_E_INVALID, "seed %d: frame index out of range", i);
+    }
   WsGuard g(p->pool);
   Workspace* w = g.w;
   if (!w) return set_err(PIGO_E_CUDA, "could not create a CUDA stream");
@@ -558,11 +588,12 @@ int pigo_puploc_run(const pigo_puploc* pc, const pigo_point* seeds, int nseeds, 
   if ((rc = ws_enter(w, st))) return rc;
   const uint8_t* d_pix = pixels;
   if (!frames_dev) {
-    const size_t bytes = (size_t)rows * dim;
+    const size_t bytes = frame_stride * (size_t)(nframes - 1) + (size_t)rows * dim;
     if ((rc = w->frames.reserve(bytes))) return rc;
     CUDA_TRY(cudaMemcpyAsync(w->frames.p, pixels, bytes, cudaMemcpyHostToDevice, st));
     d_pix = (const uint8_t*)w->frames.p;
   }
+  const int32_t* d_sf = seed_frame;
   const pigo_point* d_seeds = seeds;
   pigo_point* d_out = out;
   const float* d_rnd = randoms;
@@ -583,11 +614,16 @@ int pigo_puploc_run(const pigo_puploc* pc, const pigo_point* seeds, int nseeds, 
       CUDA_TRY(cudaMemcpyAsync(w->scratch_c.p, flipv, nseeds, cudaMemcpyHostToDevice, st));
       d_flip = (const uint8_t*)w->scratch_c.p;
     }
+    if (seed_frame) {
+      if ((rc = w->nout.reserve((size_t)nseeds * 4))) return rc;
+      CUDA_TRY(cudaMemcpyAsync(w->nout.p, seed_frame, (size_t)nseeds * 4, cudaMemcpyHostToDevice, st));
+      d_sf = (const int32_t*)w->nout.p;
+    }
   }
   int rot_slot = -1;
   if (angle > 0.0) rot_slot = (int)(32.0 * (angle > 1.0 ? 1.0 : angle));  // core/puploc.go:252-256, :166
   timing_begin(T_PUPLOC, st);
-  launch_puploc(p->tab, d_seeds, nseeds, d_rnd, rng_seed, d_pix, rows, cols, dim, rot_slot, d_flip, d_out, st);
+  launch_puploc(p->tab, d_seeds, nseeds, d_rnd, rng_seed, d_pix, d_sf, frame_stride, rows, cols, dim, rot_slot, d_flip, d_out, st);
   timing_end(T_PUPLOC, st);
   g_launches++;
   CUDA_TRY(cudaGetLastError());

@@ -202,8 +202,8 @@ void launch_finalize(const RawDet* raw, const int32_t* raw_count, int cap, const
 void launch_cluster(pigo_det* dets, const int32_t* n_in, int cap, double thr, pigo_det* tmp, uint8_t* flags, int32_t* seeds,
                     pigo_det* out, int out_cap, int32_t* n_out, int nframes, cudaStream_t st);
 void launch_puploc(const PuplocTables& T, const pigo_point* seeds, int nseeds, const float* randoms, uint64_t rng_seed,
-                   const uint8_t* pixels, int rows, int cols, int dim, int rot_slot, const uint8_t* flipv, pigo_point* out,
-                   cudaStream_t st);
+                   const uint8_t* frames, const int32_t* seed_frame, size_t frame_stride, int rows, int cols, int dim, int rot_slot,
+                   const uint8_t* flipv, pigo_point* out, cudaStream_t st);
 int build_tiled_tables(const FaceTables& tab, const std::vector<int8_t>& codes, const std::vector<float>& preds,
                        const std::vector<float>& thr, DevBuf& out);
 int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long long* d_work, cudaStream_t st, int num_sms);

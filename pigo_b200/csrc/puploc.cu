@@ -34,11 +34,13 @@ __device__ __forceinline__ uint32_t mix64(uint64_t x) {
 // together with the node's pixel pair (child-pair prefetch).
 __global__ void __launch_bounds__(1024, 1) puploc_kernel(PuplocTables T, const pigo_point* __restrict__ seeds, int nseeds,
                                                          const float* __restrict__ randoms, uint64_t rng_seed,
-                                                         const uint8_t* __restrict__ pixels, int nrows, int ncols, int dim,
+                                                         const uint8_t* __restrict__ frames, const int32_t* __restrict__ seed_frame,
+                                                         size_t frame_stride, int nrows, int ncols, int dim,
                                                          int rot_slot, const uint8_t* __restrict__ flipv_arr,
                                                          pigo_point* __restrict__ out) {
   const unsigned FULL = 0xffffffffu;
   const int sidx = blockIdx.x;
+  const uint8_t* __restrict__ pixels = frames + (seed_frame ? (size_t)seed_frame[sidx] * frame_stride : 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ float rows_[64], cols_[64], scal_[64];
   const pigo_point seed = seeds[sidx];
@@ -141,9 +143,10 @@ __global__ void __launch_bounds__(1024, 1) puploc_kernel(PuplocTables T, const p
 }
 
 void launch_puploc(const PuplocTables& T, const pigo_point* seeds, int nseeds, const float* randoms, uint64_t rng_seed,
-                   const uint8_t* pixels, int rows, int cols, int dim, int rot_slot, const uint8_t* flipv, pigo_point* out,
-                   cudaStream_t st) {
-  puploc_kernel<<<nseeds, 1024, 0, st>>>(T, seeds, nseeds, randoms, rng_seed, pixels, rows, cols, dim, rot_slot, flipv, out);
+                   const uint8_t* frames, const int32_t* seed_frame, size_t frame_stride, int rows, int cols, int dim, int rot_slot,
+                   const uint8_t* flipv, pigo_point* out, cudaStream_t st) {
+  puploc_kernel<<<nseeds, 1024, 0, st>>>(T, seeds, nseeds, randoms, rng_seed, frames, seed_frame, frame_stride, rows, cols, dim, rot_slot,
+                                         flipv, out);
 }
 
 }  // namespace pigo

@@ -45,47 +45,62 @@ def landmark_calls():
 def detect_batch(clf: Pigo, plc: PuplocCascade, flpcs: Dict[str, PuplocCascade], frames: np.ndarray, cp: CascadeParams,
                  iou: float = 0.1, min_face: int = 50, eye_perturbs: int = 50, flp_perturbs: int = 63,
                  randoms_for: Optional[Callable[[int, int], np.ndarray]] = None) -> List[List[Face]]:
-    """Per frame: one batched RunCascade for all frames, ClusterDetections, then ONE RunDetector launch for the eye seeds
-    of all faces of the frame and ONE launch per (landmark cascade) for all faces and both flips -- the per-call results
-    are identical to calling GetLandmarkPoint face by face (each seed carries its own randoms / RNG key)."""
-    from . import landmark_seed_host
+    """The frames are uploaded ONCE (DeviceFrames) and stay resident; then: one batched RunCascade, one batched
+    ClusterDetections, ONE RunDetector launch for the eye seeds of all faces of all frames, and one launch per landmark
+    cascade for all faces, both flips, all frames.  Per-call results are identical to calling RunDetector /
+    GetLandmarkPoint face by face as the reference's test does (each seed carries its own randoms / RNG key)."""
+    from . import DeviceFrames, landmark_seed_host
     frames = np.ascontiguousarray(frames, dtype=np.uint8)
-    dets, cnt = clf.RunCascadeBatch(frames, cp, 0.0)
-    out: List[List[Face]] = []
-    calls = landmark_calls()
-    for f in range(frames.shape[0]):
-        img = ImageParams(frames[f], cp.ImageParams.Rows, cp.ImageParams.Cols, cp.ImageParams.Dim)
-        _, clusters = clf.cluster_array(dets[f, :cnt[f]].copy(), iou)
-        faces = [Face((int(c["row"]), int(c["col"]), int(c["scale"]), float(c["q"]))) for c in clusters]
-        big = [k for k, c in enumerate(clusters) if c["scale"] > min_face]
-        # call indices follow the reference's sequential order: per face 2 eye calls, then the 15 landmark calls
-        base = {k: i * (2 + len(calls)) for i, k in enumerate(big)}
-        if big:
-            seeds, rnds = [], []
-            for k in big:
-                c = clusters[k]
-                ls, rs = eye_seeds(int(c["row"]), int(c["col"]), int(c["scale"]), eye_perturbs)
-                seeds += [ls, rs]
-                if randoms_for:
-                    rnds += [randoms_for(f, base[k]), randoms_for(f, base[k] + 1)]
-            eyes = plc.run_detector_batch(seeds, img, 0.0, [False] * len(seeds), np.stack(rnds) if randoms_for else None, rng_seed=1000 * f)
-            for i, k in enumerate(big):
-                faces[k].left_eye, faces[k].right_eye = eyes[2 * i], eyes[2 * i + 1]
-                faces[k].landmarks = [None] * len(calls)
-            for name in sorted(set(n for n, _ in calls)):
-                seeds, flips, rnds, where = [], [], [], []
-                for k in big:
-                    for ci, (n, flip) in enumerate(calls):
-                        if n != name:
-                            continue
-                        seeds.append(landmark_seed_host(faces[k].left_eye, faces[k].right_eye, flp_perturbs))
-                        flips.append(flip)
-                        where.append((k, ci))
-                        if randoms_for:
-                            rnds.append(randoms_for(f, base[k] + 2 + ci))
-                pts = flpcs[name].run_detector_batch(seeds, img, 0.0, flips, np.stack(rnds) if randoms_for else None,
-                                                     rng_seed=1000 * f + 7)
-                for (k, ci), p in zip(where, pts):
-                    faces[k].landmarks[ci] = p
-        out.append(faces)
-    return out
+    nf = frames.shape[0]
+    rows, cols, dim = cp.ImageParams.Rows, cp.ImageParams.Cols, cp.ImageParams.Dim
+    df = DeviceFrames(frames)
+    try:
+        dets, cnt = clf.RunCascadeBatch(df, cp, 0.0)
+        clusters, ncl = clf.cluster_batch_array(dets, cnt, iou)
+        calls = landmark_calls()
+        out: List[List[Face]] = []
+        big = []            # (frame, face index, call-index base)
+        for f in range(nf):
+            faces = [Face((int(c["row"]), int(c["col"]), int(c["scale"]), float(c["q"]))) for c in clusters[f, :ncl[f]]]
+            out.append(faces)
+            # call indices follow the reference's sequential order inside a frame: per face 2 eye calls, then 15 landmark calls
+            nb = 0
+            for k, fc in enumerate(faces):
+                if fc.det[2] > min_face:
+                    big.append((f, k, nb * (2 + len(calls))))
+                    nb += 1
+        if not big:
+            return out
+
+        def run(casc, seeds, seed_frames, flips, rnds, key):
+            return casc.run_detector_frames(seeds, seed_frames, df.ptr, nf, df.stride, rows, cols, dim, 0.0, flips,
+                                            np.stack(rnds) if randoms_for else None, rng_seed=key, frames_on_device=True)
+
+        seeds, sfr, rnds = [], [], []
+        for f, k, base in big:
+            r, c, sc, _ = out[f][k].det
+            ls, rs = eye_seeds(r, c, sc, eye_perturbs)
+            seeds += [ls, rs]; sfr += [f, f]
+            if randoms_for:
+                rnds += [randoms_for(f, base), randoms_for(f, base + 1)]
+        eyes = run(plc, seeds, sfr, [False] * len(seeds), rnds, 1)
+        for i, (f, k, base) in enumerate(big):
+            out[f][k].left_eye, out[f][k].right_eye = eyes[2 * i], eyes[2 * i + 1]
+            out[f][k].landmarks = [None] * len(calls)
+        for name in sorted(set(n for n, _ in calls)):
+            seeds, sfr, flips, rnds, where = [], [], [], [], []
+            for f, k, base in big:
+                fc = out[f][k]
+                for ci, (n, flip) in enumerate(calls):
+                    if n != name:
+                        continue
+                    seeds.append(landmark_seed_host(fc.left_eye, fc.right_eye, flp_perturbs))
+                    sfr.append(f); flips.append(flip); where.append((f, k, ci))
+                    if randoms_for:
+                        rnds.append(randoms_for(f, base + 2 + ci))
+            pts = run(flpcs[name], seeds, sfr, flips, rnds, 7)
+            for (f, k, ci), p in zip(where, pts):
+                out[f][k].landmarks[ci] = p
+        return out
+    finally:
+        df.free()

@@ -51,7 +51,7 @@ def main():
     plc = pigo_b200.NewPuplocCascade().UnpackCascade(pigo_b200.load_cascade("puploc"))
     names = sorted(set(pipeline.EYE_CASCADES + pipeline.MOUTH_CASCADES))
     flp = {n: pigo_b200.NewPuplocCascade().UnpackCascade(pigo_b200.load_cascade("lps/" + n)) for n in names}
-    nfp = 16
+    nfp = 64
     fr = np.stack([synth.frame_faces(None, 1080, 1920, shift=(37 * i, 53 * i), noise_seed=100 + i) for i in range(nfp)])
     cp = CascadeParams(ImageParams(None, 1080, 1920, 1920), 20, 1000, 0.2, 1.1)
     pipeline.detect_batch(clf, plc, flp, fr[:2], cp)
@@ -61,8 +61,8 @@ def main():
     nfaces = sum(1 for f in res for face in f if face.left_eye is not None)
     out["configs4_pipeline_host_api"] = {"frames": nfp, "seconds": dt, "frames_per_s": nfp / dt, "faces_with_landmarks": nfaces,
                                          "landmark_points": sum(len(face.landmarks) for f in res for face in f),
-                                         "note": "host-sequenced (one RunDetector/GetLandmarkPoint call per face part, each with its own H2D copy); "
-                                                 "the device-side fused pipeline is section 8f N1 (next)"}
+                                         "note": "frames uploaded once; batched RunCascade + ClusterDetections, one RunDetector launch for all eye seeds and "
+                                                 "one per landmark cascade for all frames (host sequencing only between the ~12 launches)"}
     # ---- RgbToGrayscale (N2), device resident, HBM-bound streaming kernel: 5 B/pixel
     npx = 64 * 1080 * 1920
     rgba = torch.randint(0, 256, (npx, 4), dtype=torch.uint8, device="cuda"); gray = torch.empty(npx, dtype=torch.uint8, device="cuda")
