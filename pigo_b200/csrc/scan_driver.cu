@@ -40,7 +40,8 @@ struct TilePlan {
   uint32_t tiles_per_frame = 0;
 };
 
-static TilePlan plan_bands(const std::vector<ScaleEntry>& plan, uint32_t tile_bytes, int max_scale, int ratio_pct) {
+static TilePlan plan_bands(const std::vector<ScaleEntry>& plan, uint32_t tile_bytes, int max_scale, int ratio_pct, int min_core,
+                           int min_core_steps) {
   TilePlan tp;
   const int n = (int)plan.size();
   int a = 0;
@@ -60,7 +61,7 @@ static TilePlan plan_bands(const std::vector<ScaleEntry>& plan, uint32_t tile_by
         if ((size_t)rows_t * pitch <= tile_bytes) core = c; else break;
       }
       const int step_max = plan[b - 1].step;
-      if (core >= 32 && core >= 3 * step_max) { best_b = b; best_core = core; }
+      if (core >= min_core && core >= min_core_steps * step_max) { best_b = b; best_core = core; }
     }
     if (best_b < 0) break;
     TileBand B{};
@@ -134,8 +135,7 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
     ScanArgs G = A;
     G.scale_lo = 0; G.scale_hi = A.nscales;
     G.chunks_per_frame = (A.wins_per_frame + G.chunk - 1) / G.chunk;
-    int per_sm = (int)g_opt.gather_ctas_per_sm.load();
-    if (per_sm <= 0) per_sm = gather_max_ctas_per_sm(A.tab.depth, rot);
+    const int per_sm = gather_max_ctas_per_sm(A.tab.depth, rot);
     const unsigned long long total_chunks = (unsigned long long)G.chunks_per_frame * A.nframes;
     const long long grid = std::max(1ll, std::min<long long>((long long)num_sms * per_sm, (long long)((total_chunks + 7) / 8)));
     timing_begin(T_GATHER, st);
@@ -189,7 +189,8 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
       const uint32_t tile_bytes = (uint32_t)(((smem_cap - tiles0) / W) & ~(size_t)127);
       int max_scale = (int)g_opt.tile_max_scale.load();
       if (max_scale <= 0) max_scale = 1 << 30;
-      const TilePlan tp = plan_bands(w->plan_host, tile_bytes, max_scale, (int)std::max<long long>(100, g_opt.tile_band_ratio.load()));
+      const TilePlan tp = plan_bands(w->plan_host, tile_bytes, max_scale, (int)std::max<long long>(100, g_opt.tile_band_ratio.load()),
+                                     (int)std::max<long long>(16, g_opt.tile_min_core.load()), (int)std::max<long long>(1, g_opt.tile_min_core_steps.load()));
       if (tp.nbands > 0) {
         TiledArgs F = T;
         F.ks = ks; F.tile_bytes = tile_bytes; F.nbands = tp.nbands;
