@@ -191,7 +191,7 @@ struct pigo_puploc {
 
 namespace pigo {
 // kernels / drivers implemented in the other .cu files
-void launch_scan_gather(const ScanArgs& A, int grid, cudaStream_t st);
+void launch_scan_gather(const ScanArgs& A, int grid, int max_scale, cudaStream_t st);
 void launch_scan_tiled(const TiledArgs& A, int grid, int threads, size_t smem, int ni, cudaStream_t st);
 int tiled_max_threads(int ni);
 void launch_gray(const uint8_t* rgba, size_t npix, uint8_t* gray, int grid, cudaStream_t st);

@@ -139,7 +139,7 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
     const unsigned long long total_chunks = (unsigned long long)G.chunks_per_frame * A.nframes;
     const long long grid = std::max(1ll, std::min<long long>((long long)num_sms * per_sm, (long long)((total_chunks + 7) / 8)));
     timing_begin(T_GATHER, st);
-    launch_scan_gather(G, (int)grid, st);
+    launch_scan_gather(G, (int)grid, w->plan_host.empty() ? 0 : w->plan_host.back().s, st);
     timing_end(T_GATHER, st);
     g_launches++;
     return check_launch("gather scan");

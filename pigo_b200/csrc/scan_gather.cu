@@ -10,6 +10,8 @@
 //
 // This is the universal path: every scale of the rotated scan (angle > 0), cascades whose tree depth is not 6, and
 // scan_mode=1.  The unrotated depth-6 scan uses the fused kernel of scan_tiled.cu (+ gather-v2 and deep kernels).
+#include <algorithm>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -41,13 +43,15 @@ __device__ __forceinline__ float walk_tree(const int8_t* __restrict__ tc, const 
 }
 
 // classifyRotatedRegion node walk (core/pigo.go:164-180).  NB: both coordinates are clamped with
-// nrows-1 (:167-171) -- reproduced on purpose.  64-bit intermediates like Go's int.
-template <int DEPTH>
+// nrows-1 (:167-171) -- reproduced on purpose.  I = long long mirrors Go's 64-bit int; I = int is chosen by the host
+// when 65536*max(rows, cols) + 2*256*128*max_scale provably fits 31 bits (every realistic frame), which halves the
+// instruction count of the coordinate arithmetic.
+template <int DEPTH, typename I>
 __device__ __forceinline__ float walk_tree_rot(const int8_t* __restrict__ tc, const float* __restrict__ tp, const uint8_t* __restrict__ frame,
-                                               int r, int c, long long qsin, long long qcos, int nrows, int dim, int depth, int leaves) {
+                                               int r, int c, I qsin, I qcos, int nrows, int dim, int depth, int leaves) {
   const int D = DEPTH ? DEPTH : depth;
-  const long long lim = nrows - 1;
-  const long long r16 = 65536ll * r, c16 = 65536ll * c;
+  const I lim = nrows - 1;
+  const I r16 = (I)65536 * r, c16 = (I)65536 * c;
   const int2* tc2 = reinterpret_cast<const int2*>(tc);
   const int2* tp2 = reinterpret_cast<const int2*>(tp);
   int idx = 1;
@@ -55,13 +59,13 @@ __device__ __forceinline__ float walk_tree_rot(const int8_t* __restrict__ tc, co
 #pragma unroll
   for (int j = 0; j < D; ++j) {
     const int2 kids = (j < D - 1) ? __ldg(tc2 + idx) : __ldg(tp2 + (idx - (leaves >> 1)));
-    const long long k0 = (int8_t)(cw), k1 = (int8_t)(cw >> 8), k2 = (int8_t)(cw >> 16), k3 = (cw >> 24);
-    long long r1 = min(lim, max(0ll, r16 + qcos * k0 - qsin * k1) >> 16);
-    long long c1 = min(lim, max(0ll, c16 + qsin * k0 + qcos * k1) >> 16);
-    long long r2 = min(lim, max(0ll, r16 + qcos * k2 - qsin * k3) >> 16);
-    long long c2 = min(lim, max(0ll, c16 + qsin * k2 + qcos * k3) >> 16);
+    const I k0 = (int8_t)(cw), k1 = (int8_t)(cw >> 8), k2 = (int8_t)(cw >> 16), k3 = (cw >> 24);
+    I r1 = min(lim, max((I)0, r16 + qcos * k0 - qsin * k1) >> 16);
+    I c1 = min(lim, max((I)0, c16 + qsin * k0 + qcos * k1) >> 16);
+    I r2 = min(lim, max((I)0, r16 + qcos * k2 - qsin * k3) >> 16);
+    I c2 = min(lim, max((I)0, c16 + qsin * k2 + qcos * k3) >> 16);
     r1 = r1 < 0 ? -r1 : r1; c1 = c1 < 0 ? -c1 : c1; r2 = r2 < 0 ? -r2 : r2; c2 = c2 < 0 ? -c2 : c2;  // abs(), :167
-    const unsigned p1 = __ldg(frame + r1 * dim + c1), p2 = __ldg(frame + r2 * dim + c2);
+    const unsigned p1 = __ldg(frame + (size_t)r1 * dim + (size_t)c1), p2 = __ldg(frame + (size_t)r2 * dim + (size_t)c2);
     const bool right = p1 <= p2;
     cw = right ? kids.y : kids.x;
     idx = 2 * idx + (right ? 1 : 0);
@@ -69,7 +73,8 @@ __device__ __forceinline__ float walk_tree_rot(const int8_t* __restrict__ tc, co
   return __int_as_float(cw);
 }
 
-template <int DEPTH, bool ROT>
+// ROT: 0 = unrotated, 1 = rotated with 64-bit coordinates, 2 = rotated with 32-bit coordinates (host-proven safe)
+template <int DEPTH, int ROT>
 __global__ void __launch_bounds__(256) scan_gather_kernel(const ScanArgs A) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -135,10 +140,12 @@ __global__ void __launch_bounds__(256) scan_gather_kernel(const ScanArgs A) {
       const int8_t* tc = T.codes + (size_t)t * code_stride;
       const float* tp = T.preds + (size_t)t * L;
       float pred;
-      if (ROT) {
+      if (ROT == 1) {
         const long long qsin = (long long)s * c_qsin[A.rot_slot];  // core/pigo.go:159
         const long long qcos = (long long)s * c_qcos[A.rot_slot];  // :160
-        pred = walk_tree_rot<DEPTH>(tc, tp, pc, r, c, qsin, qcos, A.rows, A.dim, T.depth, L);
+        pred = walk_tree_rot<DEPTH, long long>(tc, tp, pc, r, c, qsin, qcos, A.rows, A.dim, T.depth, L);
+      } else if (ROT == 2) {
+        pred = walk_tree_rot<DEPTH, int>(tc, tp, pc, r, c, s * c_qsin[A.rot_slot], s * c_qcos[A.rot_slot], A.rows, A.dim, T.depth, L);
       } else {
         pred = walk_tree<DEPTH>(tc, tp, pc, s, A.dim, T.depth, L);
       }
@@ -158,14 +165,22 @@ __global__ void __launch_bounds__(256) scan_gather_kernel(const ScanArgs A) {
   }
 }
 
-void launch_scan_gather(const ScanArgs& A, int grid, cudaStream_t st) {
-  const bool rot = A.rot_slot >= 0;
+static bool rot32_safe(const ScanArgs& A, int max_scale) {
+  // |65536*coord| + |qcos*k| + |qsin*k| <= 65536*max(rows, cols) + 2 * (256*max_scale) * 128  must stay below 2^31
+  const long long bound = 65536ll * std::max(A.rows, A.cols) + 2ll * 256 * 128 * (long long)max_scale;
+  return bound < 0x7fffffffll;
+}
+
+void launch_scan_gather(const ScanArgs& A, int grid, int max_scale, cudaStream_t st) {
+  const int rot = A.rot_slot < 0 ? 0 : (rot32_safe(A, max_scale) ? 2 : 1);
   if (A.tab.depth == 6) {
-    if (rot) scan_gather_kernel<6, true><<<grid, 256, 0, st>>>(A);
-    else scan_gather_kernel<6, false><<<grid, 256, 0, st>>>(A);
+    if (rot == 2) scan_gather_kernel<6, 2><<<grid, 256, 0, st>>>(A);
+    else if (rot == 1) scan_gather_kernel<6, 1><<<grid, 256, 0, st>>>(A);
+    else scan_gather_kernel<6, 0><<<grid, 256, 0, st>>>(A);
   } else {
-    if (rot) scan_gather_kernel<0, true><<<grid, 256, 0, st>>>(A);
-    else scan_gather_kernel<0, false><<<grid, 256, 0, st>>>(A);
+    if (rot == 2) scan_gather_kernel<0, 2><<<grid, 256, 0, st>>>(A);
+    else if (rot == 1) scan_gather_kernel<0, 1><<<grid, 256, 0, st>>>(A);
+    else scan_gather_kernel<0, 0><<<grid, 256, 0, st>>>(A);
   }
 }
 
@@ -175,8 +190,8 @@ namespace pigo {
 int gather_max_ctas_per_sm(int depth, bool rot) {
   int n = 0;
   const void* f;
-  if (depth == 6) f = rot ? (const void*)scan_gather_kernel<6, true> : (const void*)scan_gather_kernel<6, false>;
-  else f = rot ? (const void*)scan_gather_kernel<0, true> : (const void*)scan_gather_kernel<0, false>;
+  if (depth == 6) f = rot ? (const void*)scan_gather_kernel<6, 1> : (const void*)scan_gather_kernel<6, 0>;
+  else f = rot ? (const void*)scan_gather_kernel<0, 1> : (const void*)scan_gather_kernel<0, 0>;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, f, 256, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 4; }
   return n;
 }

@@ -437,3 +437,14 @@ def test_synthetic_cascades_other_depths_and_sizes(depth, ntrees, restore_option
             g = clf.run_cascade_array(cp_of(img, 300, 420, 420, prm), ang, cap=64)
             o = ora.run_cascade(img, 300, 420, 420, *prm, ang, cap=1 << 18)
             assert_same(g, o)
+
+
+def test_rotated_very_wide_frame_uses_64bit_coordinates(gpu_face, oracle_face):
+    """cols > 32767: 65536*col no longer fits 31 bits, the rotated kernel must fall back to 64-bit coordinates (Go's int)."""
+    img = synth.frame_noise(48, 33000, seed=12)
+    img[:, ::7] //= 3
+    for a in (0.3, 0.8):
+        g = gpu_face.run_cascade_array(cp_of(img, 48, 33000, 33000, (20, 40, 0.2, 1.2)), a)
+        assert_same(g, oracle_face.run_cascade(img, 48, 33000, 33000, 20, 40, 0.2, 1.2, a))
+    g = gpu_face.run_cascade_array(cp_of(img, 48, 33000, 33000, (20, 40, 0.2, 1.2)), 0.0)
+    assert_same(g, oracle_face.run_cascade(img, 48, 33000, 33000, 20, 40, 0.2, 1.2, 0.0))
