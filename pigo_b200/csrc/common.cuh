@@ -117,7 +117,7 @@ struct TiledArgs {
   unsigned long long* gather_counter;
   unsigned long long* q1_counter;         // consumer cursor of Q1 (gather-v2 kernel only)
   int32_t gb_shift;                       // log2 of the gather block edge in windows (4 -> 16x16, 3 -> 8x8)
-  int32_t pad5;
+  int32_t tile_prefetch;                  // tile role: fetch both children of a node with one 64-bit load
   int32_t consume_q1;                     // gather-v2 only: drain the straggler queue Q1 (complete at launch)
   int32_t gather_ni;                      // windows per lane in the gather role (ILP)
 };

@@ -10,14 +10,14 @@
 
 namespace pigo {
 
-// GROUP = lanes (= trees per step) per window: 32 -> one window per warp; 16 -> two windows per warp, each half-warp
-// an independent 16-lane group (all sync ops use the half's mask), which halves the speculation past the rejecting
+// GROUP = lanes (= trees per step) per window: 32 -> one window per warp; 16 / 8 -> two / four windows per warp, each
+// an independent lane group (all sync ops use the half's mask), which halves the speculation past the rejecting
 // tree and doubles the windows in flight per warp.
 template <int GROUP>
 __global__ void __launch_bounds__(256) deep_kernel(const ScanArgs A, unsigned long long* counter) {
   const int lane = threadIdx.x & 31;
   const int sub = lane & (GROUP - 1);
-  const unsigned gmask = GROUP == 32 ? 0xffffffffu : (0xffffu << (lane & 16));
+  const unsigned gmask = GROUP == 32 ? 0xffffffffu : (GROUP == 16 ? (0xffffu << (lane & 16)) : (0xffu << (lane & 24)));
   const int leader = lane & ~(GROUP - 1);
   const FaceTables T = A.tab;
   const uint32_t qn = min(*A.long_count, A.long_cap);
@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(256) deep_kernel(const ScanArgs A, unsigned lo
 }
 
 void launch_deep(const ScanArgs& A, unsigned long long* counter, int grid, int group, cudaStream_t st) {
-  if (group == 16) deep_kernel<16><<<grid, 256, 0, st>>>(A, counter);
+  if (group == 8) deep_kernel<8><<<grid, 256, 0, st>>>(A, counter);
+  else if (group == 16) deep_kernel<16><<<grid, 256, 0, st>>>(A, counter);
   else deep_kernel<32><<<grid, 256, 0, st>>>(A, counter);
 }
 

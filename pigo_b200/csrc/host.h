@@ -37,8 +37,9 @@ struct Options {
   std::atomic<long long> fused_smem_kb{0};  // cap on the fused kernel's shared memory (0 = all 227 KB)
   std::atomic<long long> tile_min_core{32};        // a band is tiled only if its core edge is at least this many pixels ...
   std::atomic<long long> tile_min_core_steps{3};   // ... and at least this many window steps of its largest scale
+  std::atomic<long long> tile_prefetch{0};  // tile warps: child-pair prefetch (64-bit node loads) vs plain 32-bit node loads
   std::atomic<long long> gather_block{0};   // gather block edge in windows: 16, 8, or 0 = auto (8 for <= 4 frames)
-  std::atomic<long long> deep_group{16};    // lanes (trees per step) per window in the deep kernel: 16 or 32
+  std::atomic<long long> deep_group{8};    // lanes (trees per step) per window in the deep kernel: 8, 16 or 32
   std::atomic<long long> sub_batch{64};     // frames per pipeline group (0 = whole batch)
   std::atomic<long long> lanes{1};          // internal streams the groups alternate between      // deep kernel keeps the cascade tail in shared memory when it fits
   std::atomic<long long> tile_tail_min{6};  // tail policy threshold
@@ -48,7 +49,7 @@ struct Options {
     if (k == "scan_mode") scan_mode = v; else if (k == "chunk") chunk = v; else if (k == "deep_tree") deep_tree = v;
     else if (k == "gather_ctas_per_sm") gather_ctas_per_sm = v; else if (k == "tile_max_scale") tile_max_scale = v;
     else if (k == "timing") { timing = v; timing_reset(); }
-    else if (k == "gather_warps") gather_warps = v; else if (k == "gather_ks") gather_ks = v; else if (k == "deep_group") deep_group = v; else if (k == "gather_block") gather_block = v; else if (k == "tile_min_core") tile_min_core = v; else if (k == "tile_min_core_steps") tile_min_core_steps = v; else if (k == "fused_smem_kb") fused_smem_kb = v; else if (k == "gather_ni") gather_ni = v; else if (k == "sub_batch") sub_batch = v; else if (k == "lanes") lanes = v;
+    else if (k == "gather_warps") gather_warps = v; else if (k == "gather_ks") gather_ks = v; else if (k == "deep_group") deep_group = v; else if (k == "gather_block") gather_block = v; else if (k == "tile_prefetch") tile_prefetch = v; else if (k == "tile_min_core") tile_min_core = v; else if (k == "tile_min_core_steps") tile_min_core_steps = v; else if (k == "fused_smem_kb") fused_smem_kb = v; else if (k == "gather_ni") gather_ni = v; else if (k == "sub_batch") sub_batch = v; else if (k == "lanes") lanes = v;
     else if (k == "tile_warps") tile_warps = v; else if (k == "tile_ni") tile_ni = v; else if (k == "tile_ks") tile_ks = v;
     else if (k == "tile_tail_min") tile_tail_min = v; else if (k == "tile_band_ratio") tile_band_ratio = v;
     else return false;
@@ -58,7 +59,7 @@ struct Options {
     if (k == "scan_mode") return scan_mode; if (k == "chunk") return chunk; if (k == "deep_tree") return deep_tree;
     if (k == "gather_ctas_per_sm") return gather_ctas_per_sm; if (k == "tile_max_scale") return tile_max_scale;
     if (k == "timing") return timing;
-    if (k == "gather_warps") return gather_warps; if (k == "gather_ks") return gather_ks; if (k == "deep_group") return deep_group; if (k == "gather_block") return gather_block; if (k == "tile_min_core") return tile_min_core; if (k == "tile_min_core_steps") return tile_min_core_steps; if (k == "fused_smem_kb") return fused_smem_kb; if (k == "gather_ni") return gather_ni; if (k == "sub_batch") return sub_batch; if (k == "lanes") return lanes;
+    if (k == "gather_warps") return gather_warps; if (k == "gather_ks") return gather_ks; if (k == "deep_group") return deep_group; if (k == "gather_block") return gather_block; if (k == "tile_prefetch") return tile_prefetch; if (k == "tile_min_core") return tile_min_core; if (k == "tile_min_core_steps") return tile_min_core_steps; if (k == "fused_smem_kb") return fused_smem_kb; if (k == "gather_ni") return gather_ni; if (k == "sub_batch") return sub_batch; if (k == "lanes") return lanes;
     if (k == "tile_warps") return tile_warps; if (k == "tile_ni") return tile_ni; if (k == "tile_ks") return tile_ks;
     if (k == "tile_tail_min") return tile_tail_min; if (k == "tile_band_ratio") return tile_band_ratio;
     if (k.rfind("t_", 0) == 0) return timing_query(k);

@@ -162,6 +162,7 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
   T.q1_counter = d_work + 2;
   T.gather_scale_lo = 0;
   T.gather_blocks_per_frame = 0;
+  T.tile_prefetch = g_opt.tile_prefetch.load() ? 1 : 0;
   T.gather_ni = (int)std::min<long long>(std::max<long long>(1, g_opt.gather_ni.load()), 3);
   // small batches (a frame or two) cannot fill the GPU with 256-window blocks: use 64-window blocks then
   T.gb_shift = (g_opt.gather_block.load() == 8 || (g_opt.gather_block.load() == 0 && A.nframes <= 4)) ? 3 : 4;

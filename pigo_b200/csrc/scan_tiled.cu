@@ -189,14 +189,15 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
     int idx[NG];
     float pred[NG], thr[NG];
     if (!__any_sync(FULL, beyond)) {
-      int cw[NG];
+      // plain walk: one 32-bit node load per level from the shared cascade prefix (the node load is ~30 cycles next to a
+      // ~600-cycle pixel gather, so prefetching it would only add shared-memory wavefronts to an L1TEX-bound kernel)
 #pragma unroll
-      for (int u = 0; u < NG; ++u) { idx[u] = 1; cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4); }
+      for (int u = 0; u < NG; ++u) idx[u] = 1;
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
-        int2 kids[NG];   // child-pair prefetch (see the tile role): one 64-bit shared load beside the two pixel gathers
+        int cw[NG];
 #pragma unroll
-        for (int u = 0; u < NG; ++u) kids[u] = *reinterpret_cast<const int2*>(smem + tbo[u] + 8 * idx[u]);
+        for (int u = 0; u < NG; ++u) cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4 * idx[u]);
         unsigned p1[NG], p2[NG];
 #pragma unroll
         for (int u = 0; u < NG; ++u) {
@@ -207,15 +208,11 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
           p2[u] = __ldg(pc[u] + o2);
         }
 #pragma unroll
-        for (int u = 0; u < NG; ++u) {
-          const bool right = p1[u] <= p2[u];
-          cw[u] = right ? kids[u].y : kids[u].x;
-          idx[u] = 2 * idx[u] + (right ? 1 : 0);
-        }
+        for (int u = 0; u < NG; ++u) idx[u] = 2 * idx[u] + (p1[u] <= p2[u] ? 1 : 0);
       }
 #pragma unroll
       for (int u = 0; u < NG; ++u) {
-        pred[u] = __int_as_float(cw[u]);
+        pred[u] = *reinterpret_cast<const float*>(smem + tbo[u] + 4 * idx[u]);
         thr[u] = *reinterpret_cast<const float*>(smem + tbo[u] + 512);
       }
     } else {
@@ -477,34 +474,58 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
 
       // ================= one tree per live item =================================================================
       if (!overflow_mode) {
-        // Child-pair prefetch: the two children of node idx sit at bytes 8*idx .. 8*idx+7 of the record (codes, or the
-        // two leaves after the last level), so they are fetched with ONE 64-bit load issued together with the pixel
-        // gathers of the current level; after the comparison a select picks the child.  That takes the node-code load
-        // off the dependent chain of every level (and the leaf load off its end).
         int idx[NI], cw[NI];
+        if (A.tile_prefetch) {
+          // Child-pair prefetch: the two children of node idx sit at bytes 8*idx .. 8*idx+7 of the record (codes, or the
+          // two leaves after the last level), so they are fetched with ONE 64-bit load issued together with the pixel
+          // gathers of the current level; a select picks the child afterwards.  Shorter dependent chain, but a 64-bit
+          // warp load costs at least two shared-memory wavefronts.
 #pragma unroll
-        for (int u = 0; u < NI; ++u) { idx[u] = 1; cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4); }
+          for (int u = 0; u < NI; ++u) { idx[u] = 1; cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4); }
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          int2 kids[NI];
+          for (int j = 0; j < 6; ++j) {
+            int2 kids[NI];
 #pragma unroll
-          for (int u = 0; u < NI; ++u) kids[u] = *reinterpret_cast<const int2*>(smem + tbo[u] + 8 * idx[u]);
-          uint32_t p1[NI], p2[NI];
+            for (int u = 0; u < NI; ++u) kids[u] = *reinterpret_cast<const int2*>(smem + tbo[u] + 8 * idx[u]);
+            uint32_t p1[NI], p2[NI];
 #pragma unroll
-          for (int u = 0; u < NI; ++u) {
-            // ((r*256 + code*s) >> 8) == r + ((code*s) >> 8)  (core/pigo.go:126-127)
-            const int s = sv[u];
-            const int o1 = ((sx0(cw[u]) * s) >> 8) * pitch + ((sx1(cw[u]) * s) >> 8);
-            const int o2 = ((sx2(cw[u]) * s) >> 8) * pitch + ((sx3(cw[u]) * s) >> 8);
-            p1[u] = smem[pb[u] + o1];
-            p2[u] = smem[pb[u] + o2];
+            for (int u = 0; u < NI; ++u) {
+              const int s = sv[u];
+              const int o1 = ((sx0(cw[u]) * s) >> 8) * pitch + ((sx1(cw[u]) * s) >> 8);
+              const int o2 = ((sx2(cw[u]) * s) >> 8) * pitch + ((sx3(cw[u]) * s) >> 8);
+              p1[u] = smem[pb[u] + o1];
+              p2[u] = smem[pb[u] + o2];
+            }
+#pragma unroll
+            for (int u = 0; u < NI; ++u) {
+              const bool right = p1[u] <= p2[u];                                  // core/pigo.go:129-135
+              cw[u] = right ? kids[u].y : kids[u].x;
+              idx[u] = 2 * idx[u] + (right ? 1 : 0);
+            }
+          }
+        } else {
+          // Plain walk: one 32-bit node load per level (fewest shared-memory wavefronts; the kernel is L1TEX-bound)
+#pragma unroll
+          for (int u = 0; u < NI; ++u) idx[u] = 1;
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+#pragma unroll
+            for (int u = 0; u < NI; ++u) cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4 * idx[u]);
+            uint32_t p1[NI], p2[NI];
+#pragma unroll
+            for (int u = 0; u < NI; ++u) {
+              // ((r*256 + code*s) >> 8) == r + ((code*s) >> 8)  (core/pigo.go:126-127)
+              const int s = sv[u];
+              const int o1 = ((sx0(cw[u]) * s) >> 8) * pitch + ((sx1(cw[u]) * s) >> 8);
+              const int o2 = ((sx2(cw[u]) * s) >> 8) * pitch + ((sx3(cw[u]) * s) >> 8);
+              p1[u] = smem[pb[u] + o1];
+              p2[u] = smem[pb[u] + o2];
+            }
+#pragma unroll
+            for (int u = 0; u < NI; ++u) idx[u] = 2 * idx[u] + (p1[u] <= p2[u] ? 1 : 0);   // core/pigo.go:129-135
           }
 #pragma unroll
-          for (int u = 0; u < NI; ++u) {
-            const bool right = p1[u] <= p2[u];                                  // core/pigo.go:129-135
-            cw[u] = right ? kids[u].y : kids[u].x;
-            idx[u] = 2 * idx[u] + (right ? 1 : 0);
-          }
+          for (int u = 0; u < NI; ++u) cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4 * idx[u]);   // leaf (words 64..127)
         }
         bool hit = false;
         float thr_last[NI];

@@ -254,7 +254,7 @@ VARIANTS = [
     {"scan_mode": 0, "gather_ni": 3, "sub_batch": 1, "lanes": 3},
     {"scan_mode": 0, "deep_group": 32, "tile_ks": 8, "gather_ks": 8},
     {"scan_mode": 0, "tile_tail_min": 33, "tile_ks": 5, "gather_ks": 7},
-    {"scan_mode": 0, "gather_block": 8},
+    {"scan_mode": 0, "gather_block": 8, "tile_prefetch": 1, "deep_group": 16},
     {"scan_mode": 0, "fused_smem_kb": 160, "tile_warps": 14, "gather_warps": 18},
     {"scan_mode": 0, "tile_warps": 4, "gather_warps": 28, "tile_max_scale": 24},
     {"scan_mode": 3, "gather_block": 16, "gather_ni": 2},
@@ -266,7 +266,7 @@ VARIANTS = [
 @pytest.fixture
 def restore_options():
     keys = ["scan_mode", "tile_ni", "tile_warps", "tile_ks", "tile_tail_min", "tile_band_ratio", "tile_max_scale", "chunk",
-            "gather_warps", "gather_ks", "gather_ni", "sub_batch", "lanes", "deep_group", "gather_block", "fused_smem_kb"]
+            "gather_warps", "gather_ks", "gather_ni", "sub_batch", "lanes", "deep_group", "gather_block", "fused_smem_kb", "tile_prefetch"]
     saved = {k: pigo_b200.get_option(k) for k in keys}
     yield
     for k, v in saved.items():
