@@ -167,6 +167,10 @@ int pigo_rgba_to_gray(const uint8_t *rgba, size_t npixels, uint8_t *gray, unsign
 /* Selects the scan implementation: 0 = auto (default), 1 = gather kernel only (every window
  * through global-memory gathers), 2 = tiled (shared-memory pixel tiles) + gather for the rest. */
 int pigo_set_option(const char *name, int64_t value);
+/* Host-only: JSON description of how RunCascade would be scheduled for this geometry (scale ladder, tile bands and
+ * their shared-memory tile geometry, first ladder entry left to the gather role).  Needs no device. */
+int pigo_describe_plan(int rows, int cols, int min_size, int max_size, double shift_factor, double scale_factor,
+                       char *json, size_t cap);
 int64_t pigo_get_option(const char *name);
 
 #if defined(__GNUC__)

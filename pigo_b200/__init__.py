@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "pigo_count_windows", "pigo_run_cascade", "pigo_run_cascade_batch", "pigo_cluster", "pigo_cluster_batch",
     "pigo_puploc_create", "pigo_puploc_destroy", "pigo_puploc_info", "pigo_puploc_run", "pigo_get_landmark_point",
     "pigo_set_option", "pigo_get_option", "pigo_rgba_to_gray", "pigo_puploc_run_frames", "pigo_device_alloc",
-    "pigo_device_free", "pigo_device_upload",
+    "pigo_device_free", "pigo_device_upload", "pigo_describe_plan",
 ]
 
 
@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
         L.pigo_device_alloc.argtypes = [C.POINTER(vp), sz]
         L.pigo_device_free.argtypes = [vp]
         L.pigo_device_upload.argtypes = [vp, vp, sz]
+        L.pigo_describe_plan.argtypes = [i, i, i, i, d, d, C.c_char_p, sz]
         L.pigo_set_option.argtypes = [C.c_char_p, C.c_int64]
         L.pigo_get_option.argtypes = [C.c_char_p]
         L.pigo_get_option.restype = C.c_int64
@@ -123,6 +124,14 @@ def get_option(name: str) -> int:
 
 def launch_count() -> int:
     return int(lib().pigo_launch_count())
+
+
+def describe_plan(rows, cols, min_size, max_size, shift_factor, scale_factor) -> dict:
+    """Host-only view of the scan schedule (tile bands, tile geometry, gather scales) for this geometry."""
+    import json
+    buf = C.create_string_buffer(1 << 20)
+    _check(lib().pigo_describe_plan(rows, cols, min_size, max_size, shift_factor, scale_factor, buf, len(buf)))
+    return json.loads(buf.value.decode())
 
 
 def count_windows(rows, cols, min_size, max_size, shift_factor, scale_factor) -> int:

@@ -292,6 +292,15 @@ int64_t pigo_count_windows(int rows, int cols, int min_size, int max_size, doubl
   return (int64_t)total;
 }
 
+int pigo_describe_plan(int rows, int cols, int min_size, int max_size, double shift_factor, double scale_factor, char* json, size_t cap) {
+  if (!json) return set_err(PIGO_E_INVALID, "null buffer");
+  std::vector<ScaleEntry> plan;
+  uint64_t total = 0;
+  int rc = build_plan(rows, cols, min_size, max_size, shift_factor, scale_factor, plan, total);
+  if (rc) return rc;
+  return describe_plan(plan, total, json, cap);
+}
+
 // ---- RunCascade ------------------------------------------------------------------------------------------
 int pigo_run_cascade_batch(const pigo_cascade* cc, const uint8_t* frames, int nframes, size_t frame_stride, int rows, int cols,
                            int dim, int min_size, int max_size, double shift_factor, double scale_factor, double angle,

@@ -70,7 +70,7 @@ struct ScanArgs {
   DeepItem* deep;
   unsigned int* deep_count;
   uint32_t deep_cap;
-  int32_t deep_tree;  // unused by the current kernels (kept for the standalone gather kernel's ABI)
+  int32_t pad1;
   // Q2 "long" queue: windows that survived the KS shared-memory-resident trees.  Consumed one-item-per-WARP
   // (32 trees evaluated in parallel) by the deep kernel, which bounds the serial chain of a full survivor.
   DeepItem* longq;

@@ -209,5 +209,6 @@ void launch_puploc(const PuplocTables& T, const pigo_point* seeds, int nseeds, c
                    const uint8_t* flipv, pigo_point* out, cudaStream_t st);
 int build_tiled_tables(const FaceTables& tab, const std::vector<int8_t>& codes, const std::vector<float>& preds,
                        const std::vector<float>& thr, DevBuf& out);
+int describe_plan(const std::vector<ScaleEntry>& plan, uint64_t wins, char* buf, size_t cap);
 int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long long* d_work, cudaStream_t st, int num_sms);
 }  // namespace pigo

@@ -4,7 +4,9 @@
 //   deep kernel      : queue Q2, one warp (or half warp) per window, 32 (16) trees per step
 //   gather kernel    : universal fallback -- rotated scan, cascades of depth != 6, scan_mode=1
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
+#include <string>
 
 #include "common.cuh"
 #include "host.h"
@@ -112,6 +114,52 @@ static int upload_block_prefix(Workspace* w, int lo, int hi, int gb_shift, cudaS
   return PIGO_OK;
 }
 
+// Host-only introspection of the scan plan (no device needed): which ladder entries go to per-warp tiles (and with what
+// tile geometry), which go to the gather role.  JSON text; used by tests/test_plan_cpu.py to check on the CPU that the
+// tiles partition the windows of their scales exactly and that every sample stays inside its tile.
+int describe_plan(const std::vector<ScaleEntry>& plan, uint64_t wins, char* buf, size_t cap) {
+  const int ni = (int)std::min<long long>(std::max<long long>(1, g_opt.tile_ni.load()), 4);
+  const int max_warps = tiled_max_threads(ni) / 32;
+  const int W = (int)std::min<long long>(std::max<long long>(0, g_opt.tile_warps.load()), max_warps);
+  const int ks = (int)std::min<long long>(std::max<long long>(1, g_opt.tile_ks.load()), 468);
+  const size_t casc_bytes = ((size_t)ks * kTreeRec + 15) & ~(size_t)15;
+  const size_t tiles0 = (384 + casc_bytes + 127) & ~(size_t)127;
+  std::string s = "{";
+  char tmp[512];
+  snprintf(tmp, sizeof(tmp), "\"nscales\": %d, \"windows\": %llu, \"tile_warps\": %d, ", (int)plan.size(), (unsigned long long)wins, W);
+  s += tmp;
+  TilePlan tp;
+  uint32_t tile_bytes = 0;
+  if (W > 0 && tiles0 + 4096 * (size_t)W < kSmemPerCta) {
+    size_t smem_cap = kSmemPerCta;
+    const long long lim_kb = g_opt.fused_smem_kb.load();
+    if (lim_kb > 0) smem_cap = std::min<size_t>(kSmemPerCta, std::max<size_t>((size_t)lim_kb * 1024, tiles0 + 4096 * (size_t)W));
+    tile_bytes = (uint32_t)(((smem_cap - tiles0) / W) & ~(size_t)127);
+    int max_scale = (int)g_opt.tile_max_scale.load();
+    if (max_scale <= 0) max_scale = 1 << 30;
+    tp = plan_bands(plan, tile_bytes, max_scale, (int)std::max<long long>(100, g_opt.tile_band_ratio.load()),
+                    (int)std::max<long long>(16, g_opt.tile_min_core.load()), (int)std::max<long long>(1, g_opt.tile_min_core_steps.load()));
+  }
+  snprintf(tmp, sizeof(tmp), "\"tile_bytes\": %u, \"first_untiled\": %d, \"bands\": [", tile_bytes, tp.first_untiled);
+  s += tmp;
+  for (int b = 0; b < tp.nbands; ++b) {
+    const TileBand& B = tp.band[b];
+    snprintf(tmp, sizeof(tmp), "%s{\"scale_lo\": %d, \"nscales\": %d, \"halo_lo\": %d, \"core\": %d, \"org_x\": %d, \"tiles_x\": %d, \"ntiles\": %d, "
+             "\"pitch\": %d, \"rows_t\": %d}", b ? ", " : "", B.scale_lo, B.nscales, B.halo_lo, B.core, B.org_x, B.tiles_x, B.ntiles, B.pitch, B.rows_t);
+    s += tmp;
+  }
+  s += "], \"scales\": [";
+  for (size_t i = 0; i < plan.size(); ++i) {
+    const ScaleEntry& e = plan[i];
+    snprintf(tmp, sizeof(tmp), "%s[%d, %d, %d, %d, %d, %u]", i ? ", " : "", e.s, e.step, e.off, e.nrows, e.ncols, e.wbase);
+    s += tmp;
+  }
+  s += "]}";
+  if (s.size() + 1 > cap) return set_err(PIGO_E_CAP, "plan description needs %zu bytes", s.size() + 1);
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return PIGO_OK;
+}
+
 static int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_err(PIGO_E_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
@@ -124,7 +172,7 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
   const long long mode = g_opt.scan_mode.load();
   // d_work (zeroed per call): [0] gather block cursor  [1] tile cursor  [2] Q1 consumer cursor  [3] Q2 consumer cursor
   //                           [4] Q1 count (u32)       [5] Q2 count (u32)  [6] chunk cursor of the standalone gather kernel
-  A.deep = nullptr; A.deep_count = (unsigned int*)(d_work + 4); A.deep_cap = 0; A.deep_tree = 0x7fffffff;
+  A.deep = nullptr; A.deep_count = (unsigned int*)(d_work + 4); A.deep_cap = 0;
   A.longq = nullptr; A.long_count = (unsigned int*)(d_work + 5); A.long_cap = 0;
   A.chunk = (uint32_t)std::max<long long>(32, g_opt.chunk.load());
   A.chunk_counter = d_work + 6;
