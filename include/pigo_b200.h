@@ -18,8 +18,9 @@
  *    are immutable after creation; compute calls on one handle may run concurrently from
  *    several OS threads (scratch comes from an internal per-handle pool).
  *  - output capacity is supplied by the caller.  If more results exist than fit, the call
- *    stores the first `cap` (in reference order), sets *n_out / n_out[i] to the REQUIRED
- *    count and returns PIGO_E_CAP; the caller retries with a larger buffer.
+ *    sets *n_out / n_out[i] to the REQUIRED count and returns PIGO_E_CAP; the stored entries
+ *    are then an unspecified subset (the scan emits unordered and sorts what fits), so the
+ *    caller retries with a buffer of the reported size (all mirrors do).
  */
 #ifndef PIGO_B200_H_
 #define PIGO_B200_H_
@@ -111,7 +112,8 @@ int pigo_run_cascade(const pigo_cascade *c, const uint8_t *pixels, int rows, int
 
 /* Additive batch form: `nframes` frames of identical geometry, `frame_stride` bytes apart.
  * out is [nframes][cap_per_frame], n_out is [nframes].  `flags` is a PIGO_* memory mask;
- * `stream` is a cudaStream_t (NULL = the library's own stream). */
+ * `stream` is a cudaStream_t (NULL = the library's own stream).  nframes <= 65535 per call; rows*dim < 2^31;
+ * at most 2^31 windows per frame. */
 int pigo_run_cascade_batch(const pigo_cascade *c, const uint8_t *frames, int nframes, size_t frame_stride,
                            int rows, int cols, int dim, int min_size, int max_size, double shift_factor,
                            double scale_factor, double angle, pigo_det *out, int cap_per_frame, int *n_out,
