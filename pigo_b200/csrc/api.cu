@@ -298,7 +298,7 @@ int pigo_describe_plan(int rows, int cols, int min_size, int max_size, double sh
   uint64_t total = 0;
   int rc = build_plan(rows, cols, min_size, max_size, shift_factor, scale_factor, plan, total);
   if (rc) return rc;
-  return describe_plan(plan, total, json, cap);
+  return describe_plan(plan, total, 468, json, cap);   // geometry of the stock 468-tree facefinder cascade
 }
 
 // ---- RunCascade ------------------------------------------------------------------------------------------

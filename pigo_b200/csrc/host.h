@@ -23,14 +23,13 @@ void timing_begin(int slot, cudaStream_t st);
 void timing_end(int slot, cudaStream_t st);
 
 struct Options {
-  std::atomic<long long> scan_mode{0};      // 0 auto, 1 gather only, 2 tiled + gather
-  std::atomic<long long> chunk{256};        // windows per work chunk of the gather kernel
-  std::atomic<long long> deep_tree{0};      // 0 = auto
+  std::atomic<long long> scan_mode{0};      // 0 auto (fused + gather-v2 + deep), 1 universal gather kernel only, 3 gather-v2 + deep only
+  std::atomic<long long> chunk{256};        // windows per work chunk of the universal gather kernel
   std::atomic<long long> gather_ctas_per_sm{4};   // CTAs per SM of the gather-v2 kernel (0 = occupancy)
-  std::atomic<long long> tile_max_scale{0}; // largest window size routed to the tiled kernel (0 = auto)
-  std::atomic<long long> tile_warps{24};    // warps (= private tile buffers) per CTA of the tiled kernel
-  std::atomic<long long> tile_ni{1};        // item slots per lane
-  std::atomic<long long> gather_warps{8};  // gather-role warps per CTA of the fused kernel (0 = separate gather launch)
+  std::atomic<long long> tile_max_scale{0}; // largest window size routed to the tile warps (0 = auto)
+  std::atomic<long long> tile_warps{24};    // warps (= private tile buffers) per CTA of the fused kernel
+  std::atomic<long long> tile_ni{1};        // item slots per lane of a tile warp
+  std::atomic<long long> gather_warps{8};   // gather-role warps per CTA of the fused kernel (0 = separate gather launch)
   std::atomic<long long> tile_ks{48};       // cascade trees resident in shared memory (fused kernel)
   std::atomic<long long> gather_ks{32};     // cascade trees resident in shared memory (gather-v2 kernel)
   std::atomic<long long> gather_ni{1};      // windows per lane in the gather role / gather-v2 kernel
@@ -39,31 +38,38 @@ struct Options {
   std::atomic<long long> tile_min_core_steps{3};   // ... and at least this many window steps of its largest scale
   std::atomic<long long> tile_prefetch{0};  // tile warps: child-pair prefetch (64-bit node loads) vs plain 32-bit node loads
   std::atomic<long long> gather_block{0};   // gather block edge in windows: 16, 8, or 0 = auto (8 for <= 4 frames)
-  std::atomic<long long> deep_group{8};    // lanes (trees per step) per window in the deep kernel: 8, 16 or 32
+  std::atomic<long long> deep_group{8};     // lanes (trees per step) per window in the deep kernel: 8, 16 or 32
   std::atomic<long long> sub_batch{64};     // frames per pipeline group (0 = whole batch)
-  std::atomic<long long> lanes{1};          // internal streams the groups alternate between      // deep kernel keeps the cascade tail in shared memory when it fits
+  std::atomic<long long> lanes{1};          // internal streams the groups alternate between
   std::atomic<long long> tile_tail_min{6};  // tail policy threshold
   std::atomic<long long> tile_band_ratio{200};  // a band spans scales up to ratio/100 x its first scale
   std::atomic<long long> timing{0};         // 1 = bracket every kernel with CUDA events (bench.py roofline pass)
+  std::atomic<long long>* find(const std::string& k) {
+    struct Entry { const char* name; std::atomic<long long> Options::*field; };
+    static const Entry table[] = {
+        {"scan_mode", &Options::scan_mode}, {"chunk", &Options::chunk}, {"gather_ctas_per_sm", &Options::gather_ctas_per_sm},
+        {"tile_max_scale", &Options::tile_max_scale}, {"tile_warps", &Options::tile_warps}, {"tile_ni", &Options::tile_ni},
+        {"gather_warps", &Options::gather_warps}, {"tile_ks", &Options::tile_ks}, {"gather_ks", &Options::gather_ks},
+        {"gather_ni", &Options::gather_ni}, {"fused_smem_kb", &Options::fused_smem_kb}, {"tile_min_core", &Options::tile_min_core},
+        {"tile_min_core_steps", &Options::tile_min_core_steps}, {"tile_prefetch", &Options::tile_prefetch},
+         {"gather_block", &Options::gather_block}, {"deep_group", &Options::deep_group},
+        {"sub_batch", &Options::sub_batch}, {"lanes", &Options::lanes}, {"tile_tail_min", &Options::tile_tail_min},
+        {"tile_band_ratio", &Options::tile_band_ratio}, {"timing", &Options::timing}};
+    for (const Entry& e : table)
+      if (k == e.name) return &(this->*e.field);
+    return nullptr;
+  }
   bool set(const std::string& k, long long v) {
-    if (k == "scan_mode") scan_mode = v; else if (k == "chunk") chunk = v; else if (k == "deep_tree") deep_tree = v;
-    else if (k == "gather_ctas_per_sm") gather_ctas_per_sm = v; else if (k == "tile_max_scale") tile_max_scale = v;
-    else if (k == "timing") { timing = v; timing_reset(); }
-    else if (k == "gather_warps") gather_warps = v; else if (k == "gather_ks") gather_ks = v; else if (k == "deep_group") deep_group = v; else if (k == "gather_block") gather_block = v; else if (k == "tile_prefetch") tile_prefetch = v; else if (k == "tile_min_core") tile_min_core = v; else if (k == "tile_min_core_steps") tile_min_core_steps = v; else if (k == "fused_smem_kb") fused_smem_kb = v; else if (k == "gather_ni") gather_ni = v; else if (k == "sub_batch") sub_batch = v; else if (k == "lanes") lanes = v;
-    else if (k == "tile_warps") tile_warps = v; else if (k == "tile_ni") tile_ni = v; else if (k == "tile_ks") tile_ks = v;
-    else if (k == "tile_tail_min") tile_tail_min = v; else if (k == "tile_band_ratio") tile_band_ratio = v;
-    else return false;
+    std::atomic<long long>* f = find(k);
+    if (!f) return false;
+    *f = v;
+    if (f == &timing) timing_reset();
     return true;
   }
-  long long get(const std::string& k) const {
-    if (k == "scan_mode") return scan_mode; if (k == "chunk") return chunk; if (k == "deep_tree") return deep_tree;
-    if (k == "gather_ctas_per_sm") return gather_ctas_per_sm; if (k == "tile_max_scale") return tile_max_scale;
-    if (k == "timing") return timing;
-    if (k == "gather_warps") return gather_warps; if (k == "gather_ks") return gather_ks; if (k == "deep_group") return deep_group; if (k == "gather_block") return gather_block; if (k == "tile_prefetch") return tile_prefetch; if (k == "tile_min_core") return tile_min_core; if (k == "tile_min_core_steps") return tile_min_core_steps; if (k == "fused_smem_kb") return fused_smem_kb; if (k == "gather_ni") return gather_ni; if (k == "sub_batch") return sub_batch; if (k == "lanes") return lanes;
-    if (k == "tile_warps") return tile_warps; if (k == "tile_ni") return tile_ni; if (k == "tile_ks") return tile_ks;
-    if (k == "tile_tail_min") return tile_tail_min; if (k == "tile_band_ratio") return tile_band_ratio;
+  long long get(const std::string& k) {
     if (k.rfind("t_", 0) == 0) return timing_query(k);
-    return -1;
+    std::atomic<long long>* f = find(k);
+    return f ? f->load() : -1;
   }
 };
 extern Options g_opt;
@@ -209,6 +215,6 @@ void launch_puploc(const PuplocTables& T, const pigo_point* seeds, int nseeds, c
                    const uint8_t* flipv, pigo_point* out, cudaStream_t st);
 int build_tiled_tables(const FaceTables& tab, const std::vector<int8_t>& codes, const std::vector<float>& preds,
                        const std::vector<float>& thr, DevBuf& out);
-int describe_plan(const std::vector<ScaleEntry>& plan, uint64_t wins, char* buf, size_t cap);
+int describe_plan(const std::vector<ScaleEntry>& plan, uint64_t wins, int ntrees, char* buf, size_t cap);
 int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long long* d_work, cudaStream_t st, int num_sms);
 }  // namespace pigo

@@ -94,6 +94,48 @@ static TilePlan plan_bands(const std::vector<ScaleEntry>& plan, uint32_t tile_by
   return tp;
 }
 
+// Shared-memory layout of the fused kernel: mbarriers (384 B) | cascade prefix | per-warp tiles (128-byte aligned).
+struct FusedLayout {
+  bool ok = false;
+  size_t tiles_off = 0;
+  uint32_t tile_bytes = 0;
+};
+static FusedLayout fused_layout(int W, int ks, size_t smem_cap_req) {
+  FusedLayout L;
+  const size_t casc_bytes = ((size_t)ks * kTreeRec + 15) & ~(size_t)15;   // TMA bulk copies move multiples of 16 bytes
+  L.tiles_off = (384 + casc_bytes + 127) & ~(size_t)127;
+  if (W <= 0 || L.tiles_off + 4096 * (size_t)W >= kSmemPerCta) return L;
+  // fused_smem_kb < 227 leaves the rest of the SM's 256 KB to L1 (which the gather warps' pixel loads live in)
+  size_t smem_cap = kSmemPerCta;
+  if (smem_cap_req > 0) smem_cap = std::min<size_t>(kSmemPerCta, std::max<size_t>(smem_cap_req, L.tiles_off + 4096 * (size_t)W));
+  L.tile_bytes = (uint32_t)(((smem_cap - L.tiles_off) / W) & ~(size_t)127);
+  L.ok = true;
+  return L;
+}
+
+// The fused kernel's schedule for one ladder under the current options: shared-memory layout + bands.  Used by run_scan and
+// by describe_plan, so the CPU-side geometry tests see exactly what the GPU will run.
+struct FusedPlan {
+  FusedLayout L;
+  TilePlan tp;
+  int W = 0, ks = 0, ni = 1;
+};
+static FusedPlan plan_fused(const std::vector<ScaleEntry>& plan, int ntrees) {
+  FusedPlan P;
+  P.ni = (int)std::min<long long>(std::max<long long>(1, g_opt.tile_ni.load()), 4);
+  const int max_warps = tiled_max_threads(P.ni) / 32;
+  P.W = (int)std::min<long long>(std::max<long long>(0, g_opt.tile_warps.load()), max_warps);
+  const long long fit = (long long)((kSmemPerCta - 512) / kTreeRec);   // what one CTA's shared memory can hold at most
+  P.ks = (int)std::min<long long>(std::min<long long>(std::max<long long>(1, g_opt.tile_ks.load()), ntrees), fit);
+  int max_scale = (int)g_opt.tile_max_scale.load();
+  if (max_scale <= 0) max_scale = 1 << 30;
+  P.L = fused_layout(P.W, P.ks, (size_t)std::max<long long>(0, g_opt.fused_smem_kb.load()) * 1024);
+  if (P.L.ok)
+    P.tp = plan_bands(plan, P.L.tile_bytes, max_scale, (int)std::max<long long>(100, g_opt.tile_band_ratio.load()),
+                      (int)std::max<long long>(16, g_opt.tile_min_core.load()), (int)std::max<long long>(1, g_opt.tile_min_core_steps.load()));
+  return P;
+}
+
 // Stores the prefix of 16x16-window blocks of the ladder entries [lo, hi) in ScaleEntry.pad and refreshes the device copy.
 static int upload_block_prefix(Workspace* w, int lo, int hi, int gb_shift, cudaStream_t st, uint32_t* blocks_per_frame) {
   uint32_t nb = 0;
@@ -117,29 +159,15 @@ static int upload_block_prefix(Workspace* w, int lo, int hi, int gb_shift, cudaS
 // Host-only introspection of the scan plan (no device needed): which ladder entries go to per-warp tiles (and with what
 // tile geometry), which go to the gather role.  JSON text; used by tests/test_plan_cpu.py to check on the CPU that the
 // tiles partition the windows of their scales exactly and that every sample stays inside its tile.
-int describe_plan(const std::vector<ScaleEntry>& plan, uint64_t wins, char* buf, size_t cap) {
-  const int ni = (int)std::min<long long>(std::max<long long>(1, g_opt.tile_ni.load()), 4);
-  const int max_warps = tiled_max_threads(ni) / 32;
-  const int W = (int)std::min<long long>(std::max<long long>(0, g_opt.tile_warps.load()), max_warps);
-  const int ks = (int)std::min<long long>(std::max<long long>(1, g_opt.tile_ks.load()), 468);
-  const size_t casc_bytes = ((size_t)ks * kTreeRec + 15) & ~(size_t)15;
-  const size_t tiles0 = (384 + casc_bytes + 127) & ~(size_t)127;
+int describe_plan(const std::vector<ScaleEntry>& plan, uint64_t wins, int ntrees, char* buf, size_t cap) {
+  const FusedPlan P = plan_fused(plan, ntrees);
+  const TilePlan& tp = P.tp;
+  const uint32_t tile_bytes = P.L.ok ? P.L.tile_bytes : 0;
   std::string s = "{";
   char tmp[512];
-  snprintf(tmp, sizeof(tmp), "\"nscales\": %d, \"windows\": %llu, \"tile_warps\": %d, ", (int)plan.size(), (unsigned long long)wins, W);
+  snprintf(tmp, sizeof(tmp), "\"nscales\": %d, \"windows\": %llu, \"tile_warps\": %d, \"tiles_off\": %zu, ", (int)plan.size(),
+           (unsigned long long)wins, P.W, P.L.tiles_off);
   s += tmp;
-  TilePlan tp;
-  uint32_t tile_bytes = 0;
-  if (W > 0 && tiles0 + 4096 * (size_t)W < kSmemPerCta) {
-    size_t smem_cap = kSmemPerCta;
-    const long long lim_kb = g_opt.fused_smem_kb.load();
-    if (lim_kb > 0) smem_cap = std::min<size_t>(kSmemPerCta, std::max<size_t>((size_t)lim_kb * 1024, tiles0 + 4096 * (size_t)W));
-    tile_bytes = (uint32_t)(((smem_cap - tiles0) / W) & ~(size_t)127);
-    int max_scale = (int)g_opt.tile_max_scale.load();
-    if (max_scale <= 0) max_scale = 1 << 30;
-    tp = plan_bands(plan, tile_bytes, max_scale, (int)std::max<long long>(100, g_opt.tile_band_ratio.load()),
-                    (int)std::max<long long>(16, g_opt.tile_min_core.load()), (int)std::max<long long>(1, g_opt.tile_min_core_steps.load()));
-  }
   snprintf(tmp, sizeof(tmp), "\"tile_bytes\": %u, \"first_untiled\": %d, \"bands\": [", tile_bytes, tp.first_untiled);
   s += tmp;
   for (int b = 0; b < tp.nbands; ++b) {
@@ -216,58 +244,44 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
   T.gb_shift = (g_opt.gather_block.load() == 8 || (g_opt.gather_block.load() == 0 && A.nframes <= 4)) ? 3 : 4;
 
   // ---- fused kernel: tile warps over the small scales (+ optional gather warps over the rest)
-  const int ni = (int)std::min<long long>(std::max<long long>(1, g_opt.tile_ni.load()), 4);
-  const int max_warps = tiled_max_threads(ni) / 32;
-  const int W = (int)std::min<long long>(std::max<long long>(0, g_opt.tile_warps.load()), max_warps);
-  int Wg = (int)std::min<long long>(std::max<long long>(0, g_opt.gather_warps.load()), max_warps - W);
   auto round_ks = [&](long long v) {
     const long long fit = (long long)((kSmemPerCta - 512) / kTreeRec);   // what one CTA's shared memory can hold at most
     return (int)std::min<long long>(std::min<long long>(std::max<long long>(1, v), A.tab.ntrees), fit);
   };
   int first_untiled = 0;
   bool blocks_done = false, tiled_ran = false;
-  if (W > 0 && mode != 3) {
-    const int ks = round_ks(g_opt.tile_ks.load());
-    const size_t casc_bytes = ((size_t)ks * kTreeRec + 15) & ~(size_t)15;   // TMA bulk copies move multiples of 16 bytes
-    const size_t tiles0 = (384 + casc_bytes + 127) & ~(size_t)127;
-    if (tiles0 + 4096 * (size_t)W < kSmemPerCta) {
-      // fused_smem_kb < 227 leaves the rest of the SM's 256 KB to L1 (what the gather warps' soft tiles live in)
-      size_t smem_cap = kSmemPerCta;
-      const long long lim_kb = g_opt.fused_smem_kb.load();
-      if (lim_kb > 0) smem_cap = std::min<size_t>(kSmemPerCta, std::max<size_t>((size_t)lim_kb * 1024, tiles0 + 4096 * (size_t)W));
-      const uint32_t tile_bytes = (uint32_t)(((smem_cap - tiles0) / W) & ~(size_t)127);
-      int max_scale = (int)g_opt.tile_max_scale.load();
-      if (max_scale <= 0) max_scale = 1 << 30;
-      const TilePlan tp = plan_bands(w->plan_host, tile_bytes, max_scale, (int)std::max<long long>(100, g_opt.tile_band_ratio.load()),
-                                     (int)std::max<long long>(16, g_opt.tile_min_core.load()), (int)std::max<long long>(1, g_opt.tile_min_core_steps.load()));
-      if (tp.nbands > 0) {
-        TiledArgs F = T;
-        F.ks = ks; F.tile_bytes = tile_bytes; F.nbands = tp.nbands;
-        F.tail_min = (int)g_opt.tile_tail_min.load();
-        for (int b = 0; b < tp.nbands; ++b) F.band[b] = tp.band[b];
-        F.tiles_per_frame = tp.tiles_per_frame;
-        F.total_tiles = (unsigned long long)tp.tiles_per_frame * A.nframes;
-        F.tile_warps = W;
-        F.consume_q1 = 0;
-        first_untiled = tp.first_untiled;
-        if (Wg > 0 && first_untiled < A.nscales) {
-          if ((rc = upload_block_prefix(w, first_untiled, A.nscales, T.gb_shift, st, &F.gather_blocks_per_frame))) return rc;
-          F.gather_scale_lo = first_untiled;
-          blocks_done = true;
-        } else {
-          Wg = 0;
-        }
-        F.aligned = ((A.dim % 16 == 0) && (A.frame_stride % 16 == 0) && (((uintptr_t)A.frames) % 16 == 0)) ? 1 : 0;
-        long long grid = num_sms;
-        if (Wg == 0) grid = std::max<long long>(1, std::min<long long>(num_sms, (long long)((F.total_tiles + W - 1) / W)));
-        const size_t smem = tiles0 + (size_t)tile_bytes * W;
-        timing_begin(T_TILED, st);
-        launch_scan_tiled(F, (int)grid, (W + Wg) * 32, smem, ni, st);
-        timing_end(T_TILED, st);
-        g_launches++;
-        if ((rc = check_launch("fused scan"))) return rc;
-        tiled_ran = true;
+  if (mode != 3) {
+    FusedPlan P = plan_fused(w->plan_host, A.tab.ntrees);
+    const TilePlan& tp = P.tp;
+    const int W = P.W;
+    int Wg = (int)std::min<long long>(std::max<long long>(0, g_opt.gather_warps.load()), tiled_max_threads(P.ni) / 32 - W);
+    if (P.L.ok && tp.nbands > 0) {
+      TiledArgs F = T;
+      F.ks = P.ks; F.tile_bytes = P.L.tile_bytes; F.nbands = tp.nbands;
+      F.tail_min = (int)g_opt.tile_tail_min.load();
+      for (int b = 0; b < tp.nbands; ++b) F.band[b] = tp.band[b];
+      F.tiles_per_frame = tp.tiles_per_frame;
+      F.total_tiles = (unsigned long long)tp.tiles_per_frame * A.nframes;
+      F.tile_warps = W;
+      F.consume_q1 = 0;
+      first_untiled = tp.first_untiled;
+      if (Wg > 0 && first_untiled < A.nscales) {
+        if ((rc = upload_block_prefix(w, first_untiled, A.nscales, T.gb_shift, st, &F.gather_blocks_per_frame))) return rc;
+        F.gather_scale_lo = first_untiled;
+        blocks_done = true;
+      } else {
+        Wg = 0;
       }
+      F.aligned = ((A.dim % 16 == 0) && (A.frame_stride % 16 == 0) && (((uintptr_t)A.frames) % 16 == 0)) ? 1 : 0;
+      long long grid = num_sms;
+      if (Wg == 0) grid = std::max<long long>(1, std::min<long long>(num_sms, (long long)((F.total_tiles + W - 1) / W)));
+      const size_t smem = P.L.tiles_off + (size_t)P.L.tile_bytes * W;
+      timing_begin(T_TILED, st);
+      launch_scan_tiled(F, (int)grid, (W + Wg) * 32, smem, P.ni, st);
+      timing_end(T_TILED, st);
+      g_launches++;
+      if ((rc = check_launch("fused scan"))) return rc;
+      tiled_ran = true;
     }
   }
 
