@@ -106,6 +106,20 @@ def cpu_reference_run(frames: np.ndarray, steps: int, warmup: int, nthreads: int
     return W * frames.shape[0] * steps / dt, dt / steps * 1e3
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout: everything else any library writes to fd 1 (NCCL prints its version
+    banner there at WARN level, torchrun children inherit the fd) is sent to stderr; the line itself goes to the saved fd."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(fd, obj):
+    sys.stdout.flush()
+    os.write(fd, (json.dumps(obj) + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -116,6 +130,7 @@ def main():
     ap.add_argument("--cpu-sample-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    out_fd = _claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -134,7 +149,7 @@ def main():
         sample = args.cpu_sample_frames or max(8, min(64, 2 * nthreads))
         frames = make_frames(sample, 0)
         v, ms = cpu_reference_run(frames, args.steps, max(args.warmup, 1), nthreads)
-        print(json.dumps({
+        _emit(out_fd, {
             "impl": "reference", "metric": "candidate windows/s on 1080p frames", "value": v, "unit": "windows/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
@@ -142,7 +157,7 @@ def main():
                              "sample": f"{sample} of the workload's 1080p frames per step, frame-parallel on {nthreads} threads "
                                        "(C restatement of core/pigo.go RunCascade; the Go reference cannot be built here)"},
             "e2e": {"value": v, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0})
         return
 
     # ------------------------------------------------------------------ our arm
@@ -153,7 +168,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (some images export NCCL_DEBUG=VERSION)
+            os.environ["NCCL_DEBUG"] = "WARN"   # errors only (they land on stderr, see _claim_stdout)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank if world > 1 else 0
@@ -317,7 +332,7 @@ def main():
                         "cannot be built in this image (no Go toolchain)"}
 
     if rank == 0:
-        print(json.dumps({
+        _emit(out_fd, {
             "metric": "candidate windows/s on 1080p frames", "value": value, "unit": "windows/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
@@ -325,7 +340,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": nf * ROWS * COLS, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "single_frame": single,
-            "detections_per_step": ndet}))
+            "detections_per_step": ndet})
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
