@@ -358,6 +358,7 @@ int pigo_run_cascade_batch(const pigo_cascade* cc, const uint8_t* frames, int nf
     d_nout = (int32_t*)w->nout.p;
   }
   if ((rc = w->raw.reserve((size_t)nframes * cap * sizeof(RawDet)))) return rc;
+  bool zero_out_staging = !out_dev;   // slots past a frame's count travel back to the host too: keep them defined (zero)
 
   // Sub-batch pipeline: the batch is cut into groups of `sub_batch` frames that alternate between `lanes` internal
   // streams.  (1) The deferred queues (Q1/Q2) of a group are consumed while its frames are still L2-resident;
@@ -428,6 +429,7 @@ int pigo_run_cascade_batch(const pigo_cascade* cc, const uint8_t* frames, int nf
       CUDA_TRY(cudaStreamWaitEvent(st, w->ev_join[l], 0));
     }
   }
+  if (zero_out_staging) CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)nframes * cap * sizeof(pigo_det), st));
   timing_begin(T_FINALIZE, st);
   launch_finalize((const RawDet*)w->raw.p, d_rawcount, cap, (const ScaleEntry*)w->plan.p, nscales, d_out, d_nout, nframes, st);
   timing_end(T_FINALIZE, st);
@@ -494,6 +496,7 @@ int pigo_cluster_batch(pigo_det* dets, const int* n, int nframes, int cap_per_fr
     d_n = dn;
     if (cap_per_frame > 0 && dets) CUDA_TRY(cudaMemcpyAsync(d_dets, dets, nd * sizeof(pigo_det), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(dn, n, (size_t)nframes * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)nframes * ocap * sizeof(pigo_det), st));   // defined padding in the host copy
   }
   timing_begin(T_CLUSTER, st);
   launch_cluster(d_dets, d_n, cap, iou_threshold, (pigo_det*)w->scratch_a.p, (uint8_t*)w->scratch_b.p, (int32_t*)w->scratch_c.p,

@@ -293,6 +293,7 @@ def test_scan_variants_agree_with_oracle(gpu_face, oracle_face, sample_gray, res
     for f in range(3):
         o = oracle_face.run_cascade(frames[f], 720, 1280, 1280, *TEST_PARAMS, 0.0)
         assert cnt[f] == len(o) and dets[f, :cnt[f]].tobytes() == o.tobytes()
+        assert not np.frombuffer(dets[f, cnt[f]:].tobytes(), dtype=np.uint8).any()   # padding past the count is zero, not stale
 
 
 def test_cpp_mirror_replays_reference_test():
