@@ -129,6 +129,7 @@ def main():
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--cpu-sample-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opts", default="", help="developer sweeps: library options as name=value,... (default: none)")
     args = ap.parse_args()
     out_fd = _claim_stdout()
 
@@ -174,6 +175,8 @@ def main():
     dev = local_rank if world > 1 else 0
     torch.cuda.set_device(dev)
     pigo_b200.init(dev)
+    for kv in filter(None, args.opts.split(",")):
+        pigo_b200.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     clf = pigo_b200.NewPigo().Unpack(pigo_b200.load_cascade("facefinder"))
     W = pigo_b200.count_windows(ROWS, COLS, *PARAMS)
     nf = args.frames
@@ -273,6 +276,7 @@ def main():
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "kernel": dom[0], "kernel_launch_ms": launch_ms, "frames_per_launch": frames_per_launch,
                     "scan_kernels_ms_per_step": scan_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                    "traffic_note": "ncu dram bytes of one captured launch (profiles/traffic_r01.json), scaled by frames per launch",
                     "kernels": kt, "note": "path is issue/latency/L2-transaction bound (2.3 algorithmic B/window), not HBM "
                     "bound; see DESIGN.md"}
 

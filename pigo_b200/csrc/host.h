@@ -39,7 +39,7 @@ struct Options {
   std::atomic<long long> tile_prefetch{0};  // tile warps: child-pair prefetch (64-bit node loads) vs plain 32-bit node loads
   std::atomic<long long> gather_block{0};   // gather block edge in windows: 16, 8, or 0 = auto (8 for <= 4 frames)
   std::atomic<long long> deep_group{8};     // lanes (trees per step) per window in the deep kernel: 8, 16 or 32
-  std::atomic<long long> sub_batch{64};     // frames per pipeline group (0 = whole batch)
+  std::atomic<long long> sub_batch{0};      // frames per pipeline group (0 = auto: 128 for resident frames, 64 for host frames)
   std::atomic<long long> lanes{1};          // internal streams the groups alternate between
   std::atomic<long long> tile_tail_min{6};  // tail policy threshold
   std::atomic<long long> tile_band_ratio{200};  // a band spans scales up to ratio/100 x its first scale
