@@ -77,11 +77,13 @@ long long timing_query(const std::string& key) {
 static int ws_enter(Workspace* w, cudaStream_t st) {
   if (!w->busy && cudaEventCreateWithFlags(&w->busy, cudaEventDisableTiming) != cudaSuccess) return set_err(PIGO_E_CUDA, "event creation failed");
   if (w->busy_valid && cudaStreamWaitEvent(st, w->busy, 0) != cudaSuccess) return set_err(PIGO_E_CUDA, "cudaStreamWaitEvent failed");
+  w->active_stream = st; w->active_stream_set = true;   // WsGuard records `busy` on it when the call ends, however it ends
   return PIGO_OK;
 }
 static int ws_leave_async(Workspace* w, cudaStream_t st) {
   if (cudaEventRecord(w->busy, st) != cudaSuccess) return set_err(PIGO_E_CUDA, "cudaEventRecord failed");
   w->busy_valid = true;
+  w->active_stream_set = false;
   return PIGO_OK;
 }
 
@@ -677,6 +679,7 @@ int pigo_rgba_to_gray(const uint8_t* rgba, size_t npixels, uint8_t* gray, unsign
   Workspace* w = g.w;
   if (!w) return set_err(PIGO_E_CUDA, "could not create a CUDA stream");
   cudaStream_t st = stream_ ? (cudaStream_t)stream_ : w->stream;
+  if ((rc = ws_enter(w, st))) return rc;   // a device-output call returns while the kernel still reads the staging buffer
   const bool in_dev = flags & PIGO_FRAMES_DEVICE, out_dev = flags & PIGO_OUT_DEVICE;
   const uint8_t* d_in = rgba;
   uint8_t* d_out = gray;

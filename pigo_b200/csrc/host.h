@@ -111,6 +111,8 @@ struct Workspace {
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t busy = nullptr;                  // last asynchronous use of this workspace (device-output calls)
   bool busy_valid = false;
+  cudaStream_t active_stream = nullptr;        // stream of the call that currently borrows this workspace (see WsGuard)
+  bool active_stream_set = false;
   cudaStream_t copy_stream = nullptr;          // H2D copies of host frames, one event per pipeline group
   std::vector<cudaEvent_t> copy_events;
   cudaEvent_t copy_event(int k) {
@@ -172,10 +174,20 @@ struct WorkspacePool {
   ~WorkspacePool() { for (auto* w : free_list) delete w; }
 };
 
+// Borrow of a workspace for one API call.  Whatever way the call ends (device-output calls return while their kernels
+// are still running; an error may return in the middle of queued work), the last stream the workspace was used on is
+// marked with the `busy` event before the workspace goes back to the pool, and the next borrower waits on it (ws_enter).
 struct WsGuard {
   WorkspacePool& pool; Workspace* w;
   WsGuard(WorkspacePool& p) : pool(p), w(p.acquire()) {}
-  ~WsGuard() { if (w) pool.release(w); }
+  ~WsGuard() {
+    if (!w) return;
+    if (w->active_stream_set) {
+      if (w->busy && cudaEventRecord(w->busy, w->active_stream) == cudaSuccess) w->busy_valid = true; else cudaGetLastError();
+      w->active_stream_set = false;
+    }
+    pool.release(w);
+  }
 };
 
 
