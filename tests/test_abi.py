@@ -67,3 +67,21 @@ def test_malformed_cascade_is_rejected_before_touching_the_device():
     with pytest.raises(pigo_b200.PigoError) as ei:
         pigo_b200.NewPigo().Unpack(bytes(bad))
     assert ei.value.status == pigo_b200.PIGO_E_INVALID
+
+
+def test_options_round_trip_and_unknown_names():
+    """pigo_set_option / pigo_get_option (no device needed): every tuning knob the docs name is readable and writable,
+    unknown names are rejected, timing counters read as zero launches before anything ran."""
+    names = ["scan_mode", "chunk", "gather_ctas_per_sm", "tile_max_scale", "tile_warps", "tile_ni", "gather_warps", "tile_ks",
+             "gather_ks", "gather_ni", "fused_smem_kb", "tile_min_core", "tile_min_core_steps", "tile_prefetch", "gather_block",
+             "deep_group", "sub_batch", "lanes", "tile_tail_min", "tile_band_ratio", "timing"]
+    for n in names:
+        old = pigo_b200.get_option(n)
+        assert old >= 0, n
+        pigo_b200.set_option(n, old + 1)
+        assert pigo_b200.get_option(n) == old + 1
+        pigo_b200.set_option(n, old)
+    assert pigo_b200.get_option("no_such_option") == -1
+    with pytest.raises(pigo_b200.PigoError):
+        pigo_b200.set_option("no_such_option", 1)
+    assert pigo_b200.get_option("t_tiled_n") == 0
