@@ -106,6 +106,33 @@ def cpu_reference_run(frames: np.ndarray, steps: int, warmup: int, nthreads: int
     return W * frames.shape[0] * steps / dt, dt / steps * 1e3
 
 
+def host_info() -> dict:
+    """CPU model / thread count of this box and whether a Go toolchain exists (it decides `kind`: "reference" needs Go)."""
+    model = None
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    try:
+        gov = subprocess.run(["go", "version"], capture_output=True, text=True, timeout=10).stdout.strip() or None
+    except Exception:
+        gov = None
+    try:
+        load = os.getloadavg()[0]
+    except OSError:
+        load = None
+    return {"cpu_model": model, "logical_cpus": os.cpu_count(), "go_version": gov, "loadavg_1m": load}
+
+
+def cpu_sample_frames(nthreads: int, requested: int) -> int:
+    """Frames per CPU step: at least 4 per thread so that every core works and the dynamic frame queue evens out the
+    class-dependent cost (round 1 fed 64 frames to 128 threads: half the cores idle)."""
+    return requested or max(16, min(512, 4 * nthreads))
+
+
 def _claim_stdout():
     """The contract is ONE JSON line on stdout: everything else any library writes to fd 1 (NCCL prints its version
     banner there at WARN level, torchrun children inherit the fd) is sent to stderr; the line itself goes to the saved fd."""
@@ -129,6 +156,8 @@ def main():
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--cpu-sample-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[3] / configs[4] blocks (developer runs)")
+    ap.add_argument("--pipeline-frames", type=int, default=64, help="frames per GPU per step of the configs[4] pipeline block")
     ap.add_argument("--opts", default="", help="developer sweeps: library options as name=value,... (default: none)")
     args = ap.parse_args()
     out_fd = _claim_stdout()
@@ -147,16 +176,20 @@ def main():
         if rank != 0:
             return
         nthreads = ncores
-        sample = args.cpu_sample_frames or max(8, min(64, 2 * nthreads))
+        sample = cpu_sample_frames(nthreads, args.cpu_sample_frames)
         frames = make_frames(sample, 0)
+        v1, _ = cpu_reference_run(frames[:min(sample, 3)], 1, 0, 1)
         v, ms = cpu_reference_run(frames, args.steps, max(args.warmup, 1), nthreads)
+        config = dict(config, frames_per_step_cpu=sample, note="reference arm: `frames_per_step_cpu` frames of the same workload per "
+                      "step on the host cores (the metric is a rate); frames_per_gpu is the GPU arm's batch")
         _emit(out_fd, {
             "impl": "reference", "metric": "candidate windows/s on 1080p frames", "value": v, "unit": "windows/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": v, "unit": "windows/s", "cores": nthreads, "kind": "port",
-                             "sample": f"{sample} of the workload's 1080p frames per step, frame-parallel on {nthreads} threads "
-                                       "(C restatement of core/pigo.go RunCascade; the Go reference cannot be built here)"},
+                             "sample": f"{sample} of the workload's 1080p frames per step, frame-parallel (dynamic queue) on {nthreads} "
+                                       "threads (C -O2 restatement of core/pigo.go RunCascade; the Go reference cannot be built here)",
+                             "single_thread_value": v1, "host": host_info()},
             "e2e": {"value": v, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0})
         return
@@ -267,16 +300,22 @@ def main():
         launch_ms = dom[1]["avg_us"] / 1e3
         achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
         traffic = None
-        try:   # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full capture
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
-            if tr.get("kernel") == dom[0]:
-                traffic = tr["dram_bytes_per_launch"] * frames_per_launch / tr["frames_per_launch"]
-        except Exception:
-            pass
+        traffic_src = None
+        for name in ("traffic_r02.json", "traffic_r01.json"):
+            try:   # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full capture
+                tr = json.load(open(os.path.join(ROOT, "profiles", name)))
+                if tr.get("kernel") == dom[0]:
+                    same = tr["frames_per_launch"] == frames_per_launch
+                    traffic = tr["dram_bytes_per_launch"] * (1.0 if same else frames_per_launch / tr["frames_per_launch"])
+                    traffic_src = f"profiles/{name}: ncu dram bytes of one captured launch of {tr['frames_per_launch']} frames" + \
+                        ("" if same else ", scaled by frames per launch")
+                    break
+            except Exception:
+                pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "kernel": dom[0], "kernel_launch_ms": launch_ms, "frames_per_launch": frames_per_launch,
                     "scan_kernels_ms_per_step": scan_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                    "traffic_note": "ncu dram bytes of one captured launch (profiles/traffic_r01.json), scaled by frames per launch",
+                    "traffic_note": traffic_src,
                     "kernels": kt, "note": "path is issue/latency/L2-transaction bound (2.3 algorithmic B/window), not HBM "
                     "bound; see DESIGN.md"}
 
@@ -324,16 +363,124 @@ def main():
         single = {"workload": "configs[1]: one 1920x1080 frame, device resident", "ms_per_frame_by_class": lat,
                   "windows_per_s": W / (med * 1e-3)}
 
+    # ---- configs[3]: 3840x2160 frames, rotated scan at EVERY table slot a = k/32 (rank 0, N=1 only: a sweep, not a scaling case)
+    config4 = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        from pigo_b200 import synth
+        R4, C4, n4 = 2160, 3840, 8
+        fr4 = np.stack([synth.frame_faces(None, R4, C4, shift=(31 * i, 17 * i), noise_seed=i) for i in range(n4)])
+        d4 = torch.from_numpy(fr4).to(f"cuda:{dev}")
+        o4 = torch.zeros((n4, 4096, 4), dtype=torch.int32, device=f"cuda:{dev}")
+        c4 = torch.zeros(n4, dtype=torch.int32, device=f"cuda:{dev}")
+        W4 = pigo_b200.count_windows(R4, C4, *PARAMS)
+        per_slot = {}
+        for k in range(0, 33):
+            ts = []
+            for it in range(5):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                clf.run_cascade_batch_device(d4.data_ptr(), n4, R4 * C4, R4, C4, C4, *PARAMS, k / 32.0, o4.data_ptr(), 4096, c4.data_ptr(), st)
+                b.record(stream)
+                torch.cuda.synchronize()
+                if it >= 2:
+                    ts.append(a.elapsed_time(b))
+            per_slot[k] = n4 * W4 / (float(np.median(ts)) * 1e-3)
+        rot = [per_slot[k] for k in range(1, 33)]
+        config4 = {"workload": f"configs[3]: {n4} x 3840x2160 frames (class F), test parameters, angle k/32 for k = 1..32 (classifyRotatedRegion), "
+                               "device resident, CUDA events, median of 3 after 2 warm-ups per slot",
+                   "windows_per_frame": W4, "unit": "windows/s", "rotated_min": min(rot), "rotated_median": float(np.median(rot)),
+                   "rotated_max": max(rot), "unrotated_angle0": per_slot[0], "per_slot": {str(k): per_slot[k] for k in range(1, 33)}}
+        del d4, o4, c4
+
+    # ---- configs[4]: face -> cluster -> 2 pupils -> 15 landmarks on 1080p class-F frames, frames sharded over the ranks,
+    #      one gather of faces + eyes + landmarks to rank 0 inside the timed step
+    config5 = None
+    if not args.no_extra:
+        from pigo_b200 import pipeline, synth
+        nf5, cap5 = args.pipeline_frames, 32
+        plc = pigo_b200.NewPuplocCascade().UnpackCascade(pigo_b200.load_cascade("puploc"))
+        names = sorted(set(pipeline.EYE_CASCADES + pipeline.MOUTH_CASCADES))
+        flp = {n: pigo_b200.NewPuplocCascade().UnpackCascade(pigo_b200.load_cascade("lps/" + n)) for n in names}
+        hs, fl = pipeline.landmark_call_arrays(flp)
+        ncalls = len(fl)
+        f5 = np.stack([synth.frame_faces(None, ROWS, COLS, shift=(37 * (i + nf5 * rank), 53 * (i + nf5 * rank)), noise_seed=100 + i + nf5 * rank)
+                       for i in range(nf5)])
+        p5 = torch.from_numpy(f5).pin_memory()
+        d5 = p5.to(f"cuda:{dev}")
+        faces5 = torch.zeros((nf5, cap5, 4), dtype=torch.int32, device=f"cuda:{dev}")
+        nfaces5 = torch.zeros(nf5, dtype=torch.int32, device=f"cuda:{dev}")
+        points5 = torch.zeros((nf5, cap5, 2 + ncalls, 4), dtype=torch.int32, device=f"cuda:{dev}")
+        prm = pigo_b200.PipelineParams(PARAMS[0], PARAMS[1], PARAMS[2], PARAMS[3], 0.0, 0.1, 50, 63, 63, 0)
+
+        def step_pipeline():
+            rc = L.pigo_detect_batch(clf._h, plc._h, hs, fl.ctypes.data, ncalls, d5.data_ptr(), nf5, ROWS * COLS, ROWS, COLS, COLS, C.byref(prm), None, 7,
+                                     faces5.data_ptr(), cap5, nfaces5.data_ptr(), points5.data_ptr(), 3, st)
+            if rc != 0:
+                raise RuntimeError(L.pigo_last_error().decode())
+            if world > 1:
+                pdist.gather_pipeline(faces5, nfaces5, points5, dst=0)
+
+        for _ in range(3):
+            step_pipeline()
+        barrier()
+        k5 = max(3, min(args.steps, 10))
+        l5 = pigo_b200.launch_count()
+        a5, b5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a5.record(stream)
+        for _ in range(k5):
+            step_pipeline()
+        b5.record(stream)
+        barrier()
+        ms5 = max_over_ranks(a5.elapsed_time(b5)) / k5
+        l5 = (pigo_b200.launch_count() - l5) // k5
+        nref = int(((faces5[:, :, 2] > 50).sum()).item())
+        # per-kernel device time of one step (separate pass)
+        pigo_b200.set_option("timing", 1)
+        step_pipeline()
+        torch.cuda.synchronize()
+        kt5 = {n: pigo_b200.get_option(f"t_{n}_ns") / 1e6 for n in ("tiled", "gather", "deep", "finalize", "cluster", "seeds", "puploc")}
+        pigo_b200.set_option("timing", 0)
+        # end to end through the host API: pinned frames in, faces + points out, every step
+        fh = np.zeros((nf5, cap5), dtype=pigo_b200.DET_DTYPE)
+        nh = np.zeros(nf5, dtype=np.int32)
+        ph = np.zeros((nf5, cap5, 2 + ncalls), dtype=pigo_b200.POINT_DTYPE)
+
+        def step_pipeline_host():
+            rc = L.pigo_detect_batch(clf._h, plc._h, hs, fl.ctypes.data, ncalls, p5.data_ptr(), nf5, ROWS * COLS, ROWS, COLS, COLS, C.byref(prm), None, 7,
+                                     fh.ctypes.data, cap5, nh.ctypes.data, ph.ctypes.data, 0, None)
+            if rc != 0:
+                raise RuntimeError(L.pigo_last_error().decode())
+        step_pipeline_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            step_pipeline_host()
+        barrier()
+        e5 = max_over_ranks((time.perf_counter() - t0) * 1e3) / 3
+        same = bool(np.array_equal(fh.view(np.int32).reshape(nf5, cap5, 4), faces5.cpu().numpy()) and
+                    np.array_equal(ph.view(np.int32).reshape(nf5, cap5, 2 + ncalls, 4), points5.cpu().numpy()))
+        if rank == 0:
+            config5 = {"workload": f"configs[4]: {nf5} x 1920x1080 class-F frames per GPU -> RunCascade -> ClusterDetections(0.1) -> 2 x RunDetector "
+                                   "(63 perturbations) -> 15 x GetLandmarkPoint (63) per face with Scale > 50, sequenced on the device "
+                                   "(pigo_detect_batch); frames sharded over the ranks, faces + eyes + landmarks gathered to rank 0 inside the step",
+                       "frames_per_gpu": nf5, "n_gpus": world, "value": nf5 * world / (ms5 * 1e-3), "unit": "frames/s", "ms_per_step": ms5,
+                       "faces_refined_rank0": nref, "landmark_points_rank0": nref * ncalls, "launches_per_step": int(l5),
+                       "kernel_ms_rank0": kt5,
+                       "e2e": {"value": nf5 * world / (e5 * 1e-3), "unit": "frames/s", "ms_per_step": e5, "h2d_bytes_per_step": nf5 * ROWS * COLS,
+                               "d2h_bytes_per_step": int(fh.nbytes + nh.nbytes + ph.nbytes), "matches_device_path": same},
+                       "gathered_bytes_per_rank": int(faces5.numel() * 4 + nfaces5.numel() * 4 + points5.numel() * 4)}
+        del d5
+
     # ---- CPU baseline (rank 0, N=1 only)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = args.cpu_sample_frames or max(8, min(64, 2 * ncores))
+        sample = min(cpu_sample_frames(ncores, args.cpu_sample_frames), nf)
         v, ms = cpu_reference_run(frames_host[:sample], 2, 1, ncores)
-        v1, ms1 = cpu_reference_run(frames_host[:4], 1, 0, 1)
+        v1, ms1 = cpu_reference_run(frames_host[:3], 1, 0, 1)
         cpu_baseline = {"value": v, "unit": "windows/s", "cores": ncores, "kind": "port",
-                        "sample": f"first {sample} frames of this workload x 2 passes, frame-parallel on {ncores} threads",
-                        "single_thread_value": v1, "note": "C restatement of core/pigo.go (oracle/); the Go reference "
-                        "cannot be built in this image (no Go toolchain)"}
+                        "sample": f"first {sample} frames of this workload x 2 passes, frame-parallel (dynamic queue) on {ncores} threads",
+                        "single_thread_value": v1, "host": host_info(), "note": "C -O2 restatement of core/pigo.go (oracle/); the Go "
+                        "reference cannot be built in this image (no Go toolchain)"}
 
     if rank == 0:
         _emit(out_fd, {
@@ -343,7 +490,7 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": nf * ROWS * COLS, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "single_frame": single,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "single_frame": single, "config4": config4, "config5": config5,
             "detections_per_step": ndet})
     if world > 1:
         import torch.distributed as dist

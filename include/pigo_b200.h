@@ -17,6 +17,10 @@
  *    (cgo rule: C keeps no Go pointer after return).  Handles own their device tables and
  *    are immutable after creation; compute calls on one handle may run concurrently from
  *    several OS threads (scratch comes from an internal per-handle pool).
+ *  - frames handed over as HOST memory must hold (rows-1)*dim + cols bytes per frame (what the reference indexes);
+ *    frames handed over as DEVICE memory (PIGO_FRAMES_DEVICE) must hold rows*dim bytes per frame.
+ *  - pigo_last_error() is thread-local: a Go caller must fetch it on the OS thread that made the failing call
+ *    (the shim brackets both with runtime.LockOSThread).
  *  - output capacity is supplied by the caller.  If more results exist than fit, the call
  *    sets *n_out / n_out[i] to the REQUIRED count and returns PIGO_E_CAP; the stored entries
  *    are then an unspecified subset (the scan emits unordered and sorts what fits), so the
@@ -36,7 +40,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define PIGO_B200_VERSION 100 /* 0.1.0 */
+#define PIGO_B200_VERSION 200 /* 0.2.0 */
 
 typedef enum {
   PIGO_OK = 0,
@@ -73,9 +77,18 @@ typedef struct pigo_puploc pigo_puploc;   /* pigo.PuplocCascade (core/puploc.go:
 /* ---- library -------------------------------------------------------------------------- */
 const char *pigo_last_error(void);
 int pigo_version(void);
-/* Binds the calling thread (and, by default, the process) to CUDA device `device`;
- * verifies it is compute capability 10.x.  Called implicitly with device 0 if omitted. */
+/* Selects CUDA device `device` (verified to be compute capability 10.x) as the device of every
+ * non-sharded entry point, process-wide; equivalent to pigo_init_devices(1u << device).  Called
+ * implicitly with device 0 if omitted.  Each entry point binds its calling thread itself, so Go
+ * callers need no runtime.LockOSThread for device affinity. */
 int pigo_init(int device);
+/* Multi-GPU (single process, no per-GPU host process needed): `device_mask` bit d
+ * selects device d.  The *_sharded entry points split their frame batch over these devices
+ * (shard g = frames [g*ceil(N/G), (g+1)*ceil(N/G)) on the g-th selected device); the lowest selected
+ * device serves the non-sharded entry points.  Handles need no re-creation: their device tables are
+ * replicated on a device at first use there.  Enables peer access between the selected devices. */
+int pigo_init_devices(unsigned device_mask);
+int pigo_device_count(void);
 int pigo_shutdown(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t pigo_launch_count(void);
@@ -87,6 +100,7 @@ int pigo_free_pinned(void *ptr);
 int pigo_device_alloc(void **ptr, size_t bytes);
 int pigo_device_free(void *ptr);
 int pigo_device_upload(void *dst_device, const void *src_host, size_t bytes);
+int pigo_device_download(void *dst_host, const void *src_device, size_t bytes);
 
 /* ---- face cascade: (*Pigo).Unpack, core/pigo.go:51-110 --------------------------------- */
 /* Parses the `facefinder` binary layout (8 ignored bytes, u32 depth, u32 ntrees, then per
@@ -118,6 +132,14 @@ int pigo_run_cascade_batch(const pigo_cascade *c, const uint8_t *frames, int nfr
                            int rows, int cols, int dim, int min_size, int max_size, double shift_factor,
                            double scale_factor, double angle, pigo_det *out, int cap_per_frame, int *n_out,
                            unsigned flags, void *stream);
+
+/* Multi-GPU form of the batch call: HOST frames (pinned memory from pigo_alloc_pinned recommended), sharded over
+ * the devices of pigo_init_devices, one host thread and one stream per device, no data-path collective; every
+ * device writes its frames' slices of `out` / `n_out`, so the result is identical to the single-GPU call.
+ * PIGO_E_CAP is reported after all shards ran (every n_out[i] then holds the required count). */
+int pigo_run_cascade_batch_sharded(const pigo_cascade *c, const uint8_t *frames, int nframes, size_t frame_stride,
+                                   int rows, int cols, int dim, int min_size, int max_size, double shift_factor,
+                                   double scale_factor, double angle, pigo_det *out, int cap_per_frame, int *n_out);
 
 /* ---- (*Pigo).ClusterDetections(detections []Detection, iouThreshold float64) []Detection,
  * core/pigo.go:262-308.  Like the reference it SORTS `dets` in place by Q ascending (ties keep
@@ -159,15 +181,62 @@ int pigo_get_landmark_point(const pigo_puploc *p, const pigo_point *left_eye, co
                             const uint8_t *pixels, int rows, int cols, int dim, int perturb, int flipv,
                             const float *randoms, uint64_t rng_seed, pigo_point *out);
 
+/* ---- face -> ClusterDetections -> pupils -> landmarks for a frame batch, sequenced ON THE DEVICE (additive;
+ * SURVEY.md section 8f row N1).  The reference's callers sequence these calls on the host, face by face:
+ * core/flploc_test.go:75-154 and cmd/pigo/main.go:369-565.  Per frame: RunCascade(angle) -> ClusterDetections(iou) ->
+ * for every cluster with Scale > min_face_scale: the two eye seeds (flploc_test.go:103-118), RunDetector(eye_perturbs,
+ * angle, flipV=false) for each, then for call c = 0..ncalls-1 GetLandmarkPoint(leftEye, rightEye, flp_perturbs,
+ * flp_flip[c]) on cascade flp[c] (the reference's sequence is 15 calls: lp46, lp44, lp42, lp38, lp312 each with flipV
+ * false then true; lp93, lp84, lp82, lp81 with false; lp84 with true).
+ * Outputs: faces[nframes][face_cap] = the clusters in the reference's order, n_faces[nframes] = number of clusters
+ * (PIGO_E_CAP if one exceeds face_cap), points[nframes][face_cap][2 + ncalls] = left eye, right eye, then the landmark
+ * calls in order; all-zero for clusters that were not refined (Scale <= min_face_scale).
+ * Perturbation randoms: `randoms` = [nframes][face_cap][2 + ncalls][63][3] float32 (the parity tests inject them),
+ * or NULL: counter-based generator keyed by (rng_seed, frame, cluster, call) -- so results do not depend on how a
+ * batch is split over calls or devices.  flags: PIGO_FRAMES_DEVICE as usual; PIGO_OUT_DEVICE makes faces, n_faces,
+ * points (and randoms) device pointers and the call asynchronous. */
+typedef struct {
+  int32_t min_size, max_size;
+  double shift_factor, scale_factor, angle, iou_threshold;
+  int32_t min_face_scale; /* 50 in the reference's callers */
+  int32_t eye_perturbs;   /* 50 (tests) / 63 (CLI) */
+  int32_t flp_perturbs;   /* 63 */
+  int32_t det_cap;        /* raw detections kept per frame before clustering; 0 = 2048; PIGO_E_CAP if exceeded */
+} pigo_pipeline_params;
+
+int pigo_detect_batch(const pigo_cascade *face, const pigo_puploc *puploc, const pigo_puploc *const *flp,
+                      const uint8_t *flp_flip, int ncalls, const uint8_t *frames, int nframes, size_t frame_stride,
+                      int rows, int cols, int dim, const pigo_pipeline_params *params, const float *randoms,
+                      uint64_t rng_seed, pigo_det *faces, int face_cap, int *n_faces, pigo_point *points,
+                      unsigned flags, void *stream);
+/* The same over the devices of pigo_init_devices (HOST buffers; frames sharded like pigo_run_cascade_batch_sharded,
+ * every device runs the whole sequence on its frames, results land in the caller's arrays in frame order). */
+int pigo_detect_batch_sharded(const pigo_cascade *face, const pigo_puploc *puploc, const pigo_puploc *const *flp,
+                              const uint8_t *flp_flip, int ncalls, const uint8_t *frames, int nframes,
+                              size_t frame_stride, int rows, int cols, int dim, const pigo_pipeline_params *params,
+                              const float *randoms, uint64_t rng_seed, pigo_det *faces, int face_cap, int *n_faces,
+                              pigo_point *points);
+
 /* ---- RgbToGrayscale(src image.Image) []uint8, core/grayscale.go:8-23, for *image.NRGBA input (what GetImage returns,
  * core/image.go:13-33): gray = uint8((0.299 r + 0.587 g + 0.114 b) / 256) in float64 on the 16-bit, alpha-premultiplied
  * channels color.NRGBA.RGBA() yields.  rgba is [npixels][4] (R,G,B,A), gray is [npixels].  flags: PIGO_FRAMES_DEVICE /
  * PIGO_OUT_DEVICE say where rgba / gray live.  (the stage just before the hot path.) */
 int pigo_rgba_to_gray(const uint8_t *rgba, size_t npixels, uint8_t *gray, unsigned flags, void *stream);
 
+/* ---- ImgToNRGBA(img image.Image) *image.NRGBA for *image.YCbCr sources, core/image.go:60-76 (what DecodeImage yields
+ * for a JPEG): per pixel color.YCbCrToRGB(Y[YOffset], Cb[COffset], Cr[COffset]) with
+ * alpha 0xff, bit-exact with Go's 16.16 fixed-point conversion.  `subsample` is image.YCbCrSubsampleRatio (0..5 = 444,
+ * 422, 420, 440, 411, 410); (min_x, min_y) = img.Rect.Min (>= 0), width/height = Rect size; the Y plane holds `height`
+ * rows of y_stride bytes, the chroma planes c_stride bytes per chroma row.  Outputs (either may be NULL): nrgba
+ * [height][width][4], gray [height][width] = RgbToGrayscale of the converted image (fused).  flags as pigo_rgba_to_gray. */
+int pigo_ycbcr_to_nrgba(const uint8_t *y, const uint8_t *cb, const uint8_t *cr, int y_stride, int c_stride,
+                        int subsample, int min_x, int min_y, int width, int height, uint8_t *nrgba, uint8_t *gray,
+                        unsigned flags, void *stream);
+
 /* ---- tuning / introspection (not part of the reference surface) ------------------------- */
-/* Selects the scan implementation: 0 = auto (default), 1 = gather kernel only (every window
- * through global-memory gathers), 2 = tiled (shared-memory pixel tiles) + gather for the rest. */
+/* Process-global developer knobs (kernel variants, group sizes, per-kernel timing): debugging and
+ * benchmarking only, NOT per handle -- set them before the first compute call and leave them alone while
+ * other threads are inside the library.  Names: pigo_b200/csrc/host.h (struct Options). */
 int pigo_set_option(const char *name, int64_t value);
 /* Host-only: JSON description of how RunCascade would be scheduled for this geometry (scale ladder, tile bands and
  * their shared-memory tile geometry, first ladder entry left to the gather role).  Needs no device. */

@@ -568,3 +568,45 @@ void oracle_rgba_to_gray(const uint8_t *rgba, int64_t npix, uint8_t *gray) {
     gray[i] = (uint8_t)((0.299 * (double)r + 0.587 * (double)g + 0.114 * (double)b) / 256);
   }
 }
+
+/* ---- core/image.go:60-76 ImgToNRGBA, *image.YCbCr case -------------------
+ * The per-pixel conversion is color.YCbCrToRGB of the Go standard library
+ * (image/color/ycbcr.go, go1.22 per the reference's go.mod:3; NOT under the
+ * reference tree), restated: 16.16 fixed point, yy1 = y*0x10101, and the
+ * "bits 24..31 all zero ? >>16 : saturate" clamp.  The reference's own test
+ * (core/image_test.go:118-138) restates the same constants with rounding and
+ * accepts +-1; tests/test_oracle_pins.py checks this function against that
+ * formula within +-1 for all six subsample ratios.
+ * Offsets: image.YCbCr.YOffset / COffset relative to Rect.Min = (min_x, min_y),
+ * min_x, min_y >= 0 (Go's x/2 truncates toward zero; a shift would not for
+ * negative coordinates).  subsample = image.YCbCrSubsampleRatio (444, 422,
+ * 420, 440, 411, 410 = 0..5). */
+static uint8_t go_sat16(int32_t v) {
+  if (((uint32_t)v & 0xff000000u) == 0) return (uint8_t)(v >> 16);
+  return (uint8_t)(~(v >> 31));
+}
+void oracle_ycbcr_to_nrgba(const uint8_t *yp, const uint8_t *cbp, const uint8_t *crp, int y_stride, int c_stride,
+                           int subsample, int min_x, int min_y, int width, int height, uint8_t *nrgba) {
+  for (int dy = 0; dy < height; dy++) {
+    for (int dx = 0; dx < width; dx++) {
+      int x = min_x + dx, y = min_y + dy;
+      int64_t siy = (int64_t)(y - min_y) * y_stride + (x - min_x);
+      int64_t sic;
+      switch (subsample) {
+        case 1: sic = (int64_t)(y - min_y) * c_stride + (x / 2 - min_x / 2); break;
+        case 2: sic = (int64_t)(y / 2 - min_y / 2) * c_stride + (x / 2 - min_x / 2); break;
+        case 3: sic = (int64_t)(y / 2 - min_y / 2) * c_stride + (x - min_x); break;
+        case 4: sic = (int64_t)(y - min_y) * c_stride + (x / 4 - min_x / 4); break;
+        case 5: sic = (int64_t)(y / 2 - min_y / 2) * c_stride + (x / 4 - min_x / 4); break;
+        default: sic = (int64_t)(y - min_y) * c_stride + (x - min_x); break;
+      }
+      int32_t yy1 = (int32_t)yp[siy] * 0x10101;
+      int32_t cb1 = (int32_t)cbp[sic] - 128, cr1 = (int32_t)crp[sic] - 128;
+      uint8_t *d = nrgba + 4 * ((int64_t)dy * width + dx);
+      d[0] = go_sat16(yy1 + 91881 * cr1);
+      d[1] = go_sat16(yy1 - 22554 * cb1 - 46802 * cr1);
+      d[2] = go_sat16(yy1 + 116130 * cb1);
+      d[3] = 0xff;
+    }
+  }
+}

@@ -42,7 +42,9 @@ ABI_SYMBOLS = [
     "pigo_count_windows", "pigo_run_cascade", "pigo_run_cascade_batch", "pigo_cluster", "pigo_cluster_batch",
     "pigo_puploc_create", "pigo_puploc_destroy", "pigo_puploc_info", "pigo_puploc_run", "pigo_get_landmark_point",
     "pigo_set_option", "pigo_get_option", "pigo_rgba_to_gray", "pigo_puploc_run_frames", "pigo_device_alloc",
-    "pigo_device_free", "pigo_device_upload", "pigo_describe_plan",
+    "pigo_device_free", "pigo_device_upload", "pigo_describe_plan", "pigo_init_devices", "pigo_device_count",
+    "pigo_device_download", "pigo_run_cascade_batch_sharded", "pigo_detect_batch", "pigo_detect_batch_sharded",
+    "pigo_ycbcr_to_nrgba",
 ]
 
 
@@ -98,6 +100,12 @@ def lib() -> C.CDLL:
         L.pigo_device_free.argtypes = [vp]
         L.pigo_device_upload.argtypes = [vp, vp, sz]
         L.pigo_describe_plan.argtypes = [i, i, i, i, d, d, C.c_char_p, sz]
+        L.pigo_init_devices.argtypes = [C.c_uint]
+        L.pigo_device_download.argtypes = [vp, vp, sz]
+        L.pigo_run_cascade_batch_sharded.argtypes = [vp, vp, i, sz, i, i, i, i, i, d, d, d, vp, i, vp]
+        L.pigo_detect_batch.argtypes = [vp, vp, vp, vp, i, vp, i, sz, i, i, i, vp, vp, u64, vp, i, vp, vp, C.c_uint, vp]
+        L.pigo_detect_batch_sharded.argtypes = [vp, vp, vp, vp, i, vp, i, sz, i, i, i, vp, vp, u64, vp, i, vp, vp]
+        L.pigo_ycbcr_to_nrgba.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, vp, vp, C.c_uint, vp]
         L.pigo_set_option.argtypes = [C.c_char_p, C.c_int64]
         L.pigo_get_option.argtypes = [C.c_char_p]
         L.pigo_get_option.restype = C.c_int64
@@ -112,6 +120,15 @@ def _check(rc: int):
 
 def init(device: int = 0):
     _check(lib().pigo_init(device))
+
+
+def init_devices(mask: int):
+    """Selects the devices of the *_sharded entry points (bit d = device d); SURVEY.md section 8e."""
+    _check(lib().pigo_init_devices(mask))
+
+
+def device_count() -> int:
+    return int(lib().pigo_device_count())
 
 
 def set_option(name: str, value: int):
@@ -267,6 +284,24 @@ class Pigo:
                                               cp.MinSize, cp.MaxSize, cp.ShiftFactor, cp.ScaleFactor, angle,
                                               out.ctypes.data, cap_per_frame, cnt.ctypes.data,
                                               FRAMES_DEVICE if on_dev else MEM_HOST, None)
+            if rc == PIGO_E_CAP:
+                cap_per_frame = int(cnt.max())
+                continue
+            _check(rc)
+            return out, cnt[:nf]
+
+    def RunCascadeBatchSharded(self, frames: np.ndarray, cp: CascadeParams, angle: float = 0.0, cap_per_frame: int = 1024):
+        """RunCascadeBatch over the devices of init_devices (host frames; identical result)."""
+        self._need()
+        img = cp.ImageParams
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        nf = frames.shape[0]
+        while True:
+            out = np.zeros((nf, max(cap_per_frame, 1)), dtype=DET_DTYPE)
+            cnt = np.zeros(max(nf, 1), dtype=np.int32)
+            rc = lib().pigo_run_cascade_batch_sharded(self._h, frames.ctypes.data, nf, frames.strides[0] if nf else 0, img.Rows, img.Cols,
+                                                      img.Dim, cp.MinSize, cp.MaxSize, cp.ShiftFactor, cp.ScaleFactor, angle,
+                                                      out.ctypes.data, cap_per_frame, cnt.ctypes.data)
             if rc == PIGO_E_CAP:
                 cap_per_frame = int(cnt.max())
                 continue
@@ -469,6 +504,27 @@ def RgbToGrayscale(rgba: np.ndarray) -> np.ndarray:
     out = np.zeros(a.shape[:-1], dtype=np.uint8)
     _check(lib().pigo_rgba_to_gray(a.ctypes.data if n else None, n, out.ctypes.data if n else None, MEM_HOST, None))
     return out
+
+
+class PipelineParams(C.Structure):
+    """pigo_pipeline_params (include/pigo_b200.h)."""
+    _fields_ = [("min_size", C.c_int32), ("max_size", C.c_int32), ("shift_factor", C.c_double), ("scale_factor", C.c_double),
+                ("angle", C.c_double), ("iou_threshold", C.c_double), ("min_face_scale", C.c_int32), ("eye_perturbs", C.c_int32),
+                ("flp_perturbs", C.c_int32), ("det_cap", C.c_int32)]
+
+
+def YCbCrToNRGBA(y: np.ndarray, cb: np.ndarray, cr: np.ndarray, subsample: int, width: int, height: int, min_x: int = 0, min_y: int = 0,
+                 want_gray: bool = False):
+    """ImgToNRGBA for an *image.YCbCr (core/image.go:60-76): y is [height][YStride], cb/cr are [chroma rows][CStride] uint8 planes laid
+    out like image.YCbCr for Rect (min_x, min_y)-(min_x+width, min_y+height); subsample = image.YCbCrSubsampleRatio (0..5).
+    Returns nrgba [height][width][4] (and gray [height][width] = RgbToGrayscale of it when want_gray)."""
+    y = np.ascontiguousarray(y, dtype=np.uint8); cb = np.ascontiguousarray(cb, dtype=np.uint8); cr = np.ascontiguousarray(cr, dtype=np.uint8)
+    out = np.zeros((height, width, 4), dtype=np.uint8)
+    gray = np.zeros((height, width), dtype=np.uint8) if want_gray else None
+    _check(lib().pigo_ycbcr_to_nrgba(y.ctypes.data, cb.ctypes.data, cr.ctypes.data, y.shape[1] if y.ndim == 2 else width,
+                                     cb.shape[1] if cb.ndim == 2 else 0, subsample, min_x, min_y, width, height,
+                                     out.ctypes.data if out.size else None, gray.ctypes.data if want_gray and gray.size else None, MEM_HOST, None))
+    return (out, gray) if want_gray else out
 
 
 class DeviceFrames:

@@ -53,10 +53,14 @@ __global__ void __launch_bounds__(256) cluster_kernel(pigo_det* __restrict__ det
 
   // ---- 2. seeds
   for (int i = 0; i < n; ++i) {
-    if (*(volatile uint8_t*)(asg + i)) continue;  // uniform: asg[] only changes between barriers below
+    // Uniform branch: asg[i] is written only inside the marking loops of EARLIER seed iterations, each of which ends in a
+    // barrier.  The seed's own flag is deliberately not set below (j != i): the reference sets assignments[i] there
+    // (IoU(i,i) = 1 > thr, core/pigo.go:290-296) but never reads it again, and setting it here would let a lagging warp
+    // of this same iteration read 1 and skip the barrier the others are waiting at.
+    if (*(volatile uint8_t*)(asg + i)) continue;
     const pigo_det di = d[i];
     for (int j = tid; j < n; j += nt)
-      if (calc_iou(di, d[j]) > thr) asg[j] = 1;
+      if (j != i && calc_iou(di, d[j]) > thr) asg[j] = 1;
     if (tid == 0) sd[s_nseeds++] = i;
     __syncthreads();
   }

@@ -45,6 +45,14 @@ struct DeepItem {
   float acc;
 };
 
+// Rotated scan (core/pigo.go:150-191).  65536*r + qcos*c0 - qsin*c1 is clamped at 0 and THEN shifted (:167), and
+//   max(0, 65536*r + x) >> 16  ==  max(0, r + (x >> 16))     for every integer r, x  (65536*r is a multiple of 65536),
+// so a node's four sample coordinates are r + dr1, c + dc1, r + dr2, c + dc2 clamped to [0, nrows-1] (BOTH with nrows-1:
+// the reference's column clamp quirk, :168,:171), where the four deltas depend only on (scale, table slot, node).
+struct RotNode {
+  int16_t dr1, dc1, dr2, dc2;
+};
+
 struct ScanArgs {
   FaceTables tab;
   const uint8_t* frames;
@@ -55,6 +63,9 @@ struct ScanArgs {
   uint32_t wins_per_frame;
   // rotated path (angle > 0): table slot int(32*a), core/pigo.go:159-160
   int32_t rot_slot;  // -1 = unrotated
+  // rotated path, table-driven kernels: per (ladder entry, tree, node) the four sample offsets of classifyRotatedRegion
+  // (core/pigo.go:167-171) precomputed for this call's slot; nullptr = not built (universal gather kernel computes them)
+  const RotNode* rot_tab;
   // outputs
   RawDet* raw;          // [nframes][cap]
   int32_t* raw_count;   // [nframes]
@@ -70,7 +81,7 @@ struct ScanArgs {
   DeepItem* deep;
   unsigned int* deep_count;
   uint32_t deep_cap;
-  int32_t pad1;
+  int32_t batch_frames;       // frames of the whole API call (group-independent choices: gather block edge, deep group width)
   // Q2 "long" queue: windows that survived the KS shared-memory-resident trees.  Consumed one-item-per-WARP
   // (32 trees evaluated in parallel) by the deep kernel, which bounds the serial chain of a full survivor.
   DeepItem* longq;

@@ -1,85 +1,171 @@
-// deep.cu -- finishes the windows that survived the KS shared-memory-resident trees (queue Q2), ONE WARP PER WINDOW,
-// ONE TREE PER LANE: lanes walk 32 consecutive trees of the same window in parallel (tree walks are independent of
-// each other -- only the early-exit test couples them), then the warp replays the reference's float32 accumulation
-// and threshold tests in tree order (core/pigo.go:137-141) with shuffles.  A full survivor of the 468-tree cascade
-// costs ~13 steps instead of a ~400-tree serial chain of dependent L2 round trips; trees evaluated past the
-// rejecting one are wasted work, acceptable because windows that reach tree KS usually live long.
+// deep.cu -- finishes the windows that survived the shared-memory-resident trees (queue Q2): ONE LANE GROUP PER WINDOW,
+// ONE TREE PER LANE.  The GROUP lanes walk GROUP consecutive trees of the same window in parallel (tree walks are
+// independent of each other -- only the early-exit test couples them), then the group replays the reference's float32
+// accumulation and threshold tests in tree order (core/pigo.go:137-141) with shuffles.  A full survivor of the 468-tree
+// cascade costs 468/GROUP steps instead of a ~420-tree serial chain of dependent L2 round trips; trees evaluated past the
+// rejecting one are wasted work, acceptable because windows that reach this kernel usually live long.
 // Bit-exactness: each lane produces the same leaf the serial walk would, and the sum is formed in the same order.
+//
+// Round 2: (1) the loop is FLAT -- every iteration each lane group either fetches its next window or walks one step, so the
+// 32/GROUP groups of a warp never wait for each other at a reconvergence point (round 1 nested "fetch { while (alive) step }",
+// ncu: 16.6 of 32 lanes active per instruction); (2) ROT variant: classifyRotatedRegion (core/pigo.go:150-191) with the
+// node's sample offsets read from the per-call table (RotNode, common.cuh) instead of being recomputed per node.
 #include "common.cuh"
 #include "host.h"
 
 namespace pigo {
 
-// GROUP = lanes (= trees per step) per window: 32 -> one window per warp; 16 / 8 -> two / four windows per warp, each
-// an independent lane group (all sync ops use the half's mask), which halves the speculation past the rejecting
-// tree and doubles the windows in flight per warp.
-template <int GROUP>
+template <int GROUP, int ROT>
 __global__ void __launch_bounds__(256) deep_kernel(const ScanArgs A, unsigned long long* counter) {
+  const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int sub = lane & (GROUP - 1);
   const unsigned gmask = GROUP == 32 ? 0xffffffffu : (GROUP == 16 ? (0xffffu << (lane & 16)) : (0xffu << (lane & 24)));
   const int leader = lane & ~(GROUP - 1);
   const FaceTables T = A.tab;
   const uint32_t qn = min(*A.long_count, A.long_cap);
+  const int lim = A.rows - 1;
+
+  bool have = false, more = true;
+  uint32_t wid = 0;
+  int frame = 0, t0 = 0, s = 0, r = 0, c = 0;
+  float acc = 0.f;
+  const uint8_t* pc = A.frames;        // unrotated: the window's centre pixel; rotated: the frame
+  const RotNode* rt = A.rot_tab;       // rotated: this scale's node table, tree 0
+
   for (;;) {
-    unsigned long long g = 0;
-    if (sub == 0) g = atomicAdd(counter, 1ull);
-    g = __shfl_sync(gmask, g, leader);
-    if (g >= qn) break;
-    const DeepItem it = A.longq[g];
-    const int si = find_scale(A.plan, A.nscales, it.wid);
-    const ScaleEntry e = A.plan[si];
-    const uint32_t local = it.wid - e.wbase;
-    const uint32_t ri = local / (uint32_t)e.ncols, ci = local - ri * (uint32_t)e.ncols;
-    const int s = e.s;
-    const uint8_t* pc = A.frames + (size_t)it.frame * A.frame_stride + (size_t)(e.off + (int)ri * e.step) * A.dim + (e.off + (int)ci * e.step);
-    int t0 = it.tree;
-    float acc = it.acc;
-    bool rejected = false;
-    float thr_prev = 0.f;
-    while (t0 < T.ntrees && !rejected) {
-      const int t = min(t0 + sub, T.ntrees - 1);      // lanes past the last tree redo it harmlessly
-      // child-pair prefetch: both children of node idx (codes: bytes 8*idx.., leaves: floats 2*idx-64..) are fetched with
-      // one 64-bit load that is in flight together with the two pixel gathers, so a level costs ONE dependent L2 round
-      // trip instead of two
-      const int2* tc2 = reinterpret_cast<const int2*>(T.codes + (size_t)t * 256);
-      const int2* tp2 = reinterpret_cast<const int2*>(T.preds + (size_t)t * 64);
-      const float thr = __ldg(T.thresh + t);
-      int idx = 1;
-      int cw = __ldg(reinterpret_cast<const int*>(tc2) + 1);
-#pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        const int2 kids = j < 5 ? __ldg(tc2 + idx) : __ldg(tp2 + (idx - 32));
-        const int o1 = (((int)(int8_t)(cw) * s) >> 8) * A.dim + (((int)(int8_t)(cw >> 8) * s) >> 8);
-        const int o2 = (((int)(int8_t)(cw >> 16) * s) >> 8) * A.dim + (((cw >> 24) * s) >> 8);
-        const unsigned p1 = __ldg(pc + o1), p2 = __ldg(pc + o2);
-        const bool right = p1 <= p2;                  // core/pigo.go:129-135
-        cw = right ? kids.y : kids.x;
-        idx = 2 * idx + (right ? 1 : 0);
+    if (!have && more) {
+      unsigned long long g = 0;
+      if (sub == 0) g = atomicAdd(counter, 1ull);
+      g = __shfl_sync(gmask, g, leader);
+      if (g >= qn) {
+        more = false;
+      } else {
+        const DeepItem it = A.longq[g];
+        const int si = find_scale(A.plan, A.nscales, it.wid);
+        const ScaleEntry e = A.plan[si];
+        const uint32_t local = it.wid - e.wbase;
+        const uint32_t ri = local / (uint32_t)e.ncols, ci = local - ri * (uint32_t)e.ncols;
+        s = e.s; wid = it.wid; frame = it.frame; t0 = it.tree; acc = it.acc;
+        r = e.off + (int)ri * e.step; c = e.off + (int)ci * e.step;
+        pc = A.frames + (size_t)it.frame * A.frame_stride;
+        if (ROT) rt = A.rot_tab + (size_t)si * T.ntrees * 64;
+        else pc += (size_t)r * A.dim + c;
+        have = true;
       }
-      const float pred = __int_as_float(cw);
+    }
+    if (!__any_sync(FULL, have)) break;
+    if (have) {
+      const int t = min(t0 + sub, T.ntrees - 1);        // lanes past the last tree redo it harmlessly
+      const float thr = __ldg(T.thresh + t);
+      const int2* tp2 = reinterpret_cast<const int2*>(T.preds + (size_t)t * 64);
+      int idx = 1;
+      float pred;
+      if (ROT) {
+        // children of node idx are nodes 2idx, 2idx+1: adjacent 8-byte records, fetched with one 16-byte load while
+        // this node's two pixels are in flight
+        const RotNode* tn = rt + (size_t)t * 64;
+        uint2 cur = __ldg(reinterpret_cast<const uint2*>(tn + 1));
+        int leafbits = 0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          uint4 kids = make_uint4(0, 0, 0, 0);
+          int2 lv = make_int2(0, 0);
+          if (j < 5) kids = __ldg(reinterpret_cast<const uint4*>(tn + 2 * idx));
+          else lv = __ldg(tp2 + (idx - 32));
+          const int r1 = __vimin_s32_relu(r + (int)(short)(cur.x & 0xffff), lim), c1 = __vimin_s32_relu(c + ((int)cur.x >> 16), lim);
+          const int r2 = __vimin_s32_relu(r + (int)(short)(cur.y & 0xffff), lim), c2 = __vimin_s32_relu(c + ((int)cur.y >> 16), lim);
+          const unsigned p1 = __ldg(pc + (size_t)r1 * A.dim + c1), p2 = __ldg(pc + (size_t)r2 * A.dim + c2);
+          const bool right = p1 <= p2;                  // core/pigo.go:179
+          cur = right ? make_uint2(kids.z, kids.w) : make_uint2(kids.x, kids.y);
+          leafbits = right ? lv.y : lv.x;
+          idx = 2 * idx + (right ? 1 : 0);
+        }
+        pred = __int_as_float(leafbits);
+      } else {
+        // child-pair prefetch: both children of node idx (codes: bytes 8*idx.., leaves: floats 2*idx-64..) are fetched
+        // with one 64-bit load that is in flight together with the two pixel gathers
+        const int2* tc2 = reinterpret_cast<const int2*>(T.codes + (size_t)t * 256);
+        int cw = __ldg(reinterpret_cast<const int*>(tc2) + 1);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int2 kids = j < 5 ? __ldg(tc2 + idx) : __ldg(tp2 + (idx - 32));
+          const int o1 = (((int)(int8_t)(cw) * s) >> 8) * A.dim + (((int)(int8_t)(cw >> 8) * s) >> 8);
+          const int o2 = (((int)(int8_t)(cw >> 16) * s) >> 8) * A.dim + (((cw >> 24) * s) >> 8);
+          const unsigned p1 = __ldg(pc + o1), p2 = __ldg(pc + o2);
+          const bool right = p1 <= p2;                  // core/pigo.go:129-135
+          cw = right ? kids.y : kids.x;
+          idx = 2 * idx + (right ? 1 : 0);
+        }
+        pred = __int_as_float(cw);
+      }
+      // the reference's sequential accumulation, core/pigo.go:137-141, branch-free over the group's GROUP trees
       const int nvalid = min(GROUP, T.ntrees - t0);
-      for (int j = 0; j < nvalid; ++j) {              // the reference's sequential accumulation, :137-141
-        acc += __shfl_sync(gmask, pred, leader + j);
-        thr_prev = __shfl_sync(gmask, thr, leader + j);
-        if (acc <= thr_prev) { rejected = true; break; }
+      bool rejected = false;
+      float thr_last = 0.f;
+#pragma unroll
+      for (int j = 0; j < GROUP; ++j) {
+        const float pj = __shfl_sync(gmask, pred, leader + j), tj = __shfl_sync(gmask, thr, leader + j);
+        if (j < nvalid && !rejected) {
+          acc += pj;
+          thr_last = tj;
+          rejected = acc <= tj;
+        }
       }
       t0 += GROUP;
-    }
-    if (!rejected && sub == 0) {
-      const float q = acc - thr_prev;                 // :144 (thr_prev == threshold of the last tree)
-      if (q > 0.0f) {                                 // :246
-        const int pos = atomicAdd(A.raw_count + it.frame, 1);
-        if (pos < A.cap) A.raw[(size_t)it.frame * A.cap + pos] = RawDet{it.wid, q};
+      if (rejected) {
+        have = false;
+      } else if (t0 >= T.ntrees) {
+        if (sub == 0) {
+          const float q = acc - thr_last;               // :144 (thr_last == threshold of the last tree)
+          if (q > 0.0f) {                               // :246
+            const int pos = atomicAdd(A.raw_count + frame, 1);
+            if (pos < A.cap) A.raw[(size_t)frame * A.cap + pos] = RawDet{wid, q};
+          }
+        }
+        have = false;
       }
     }
   }
 }
 
 void launch_deep(const ScanArgs& A, unsigned long long* counter, int grid, int group, cudaStream_t st) {
-  if (group == 8) deep_kernel<8><<<grid, 256, 0, st>>>(A, counter);
-  else if (group == 16) deep_kernel<16><<<grid, 256, 0, st>>>(A, counter);
-  else deep_kernel<32><<<grid, 256, 0, st>>>(A, counter);
+  const bool rot = A.rot_slot >= 0 && A.rot_tab != nullptr;
+  if (rot) {
+    if (group == 8) deep_kernel<8, 1><<<grid, 256, 0, st>>>(A, counter);
+    else if (group == 16) deep_kernel<16, 1><<<grid, 256, 0, st>>>(A, counter);
+    else deep_kernel<32, 1><<<grid, 256, 0, st>>>(A, counter);
+  } else {
+    if (group == 8) deep_kernel<8, 0><<<grid, 256, 0, st>>>(A, counter);
+    else if (group == 16) deep_kernel<16, 0><<<grid, 256, 0, st>>>(A, counter);
+    else deep_kernel<32, 0><<<grid, 256, 0, st>>>(A, counter);
+  }
+}
+
+// ---- rotated node table -------------------------------------------------------------------------------------
+// One thread per (ladder entry, tree, node): the four deltas of core/pigo.go:167-171 in Go's 64-bit int arithmetic.
+__global__ void __launch_bounds__(256) rot_table_kernel(FaceTables T, const ScaleEntry* __restrict__ plan, int nscales, int slot,
+                                                        RotNode* __restrict__ out) {
+  const size_t total = (size_t)nscales * T.ntrees * 64;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int idx = (int)(i & 63);
+    const size_t st = i >> 6;
+    const int t = (int)(st % (size_t)T.ntrees), si = (int)(st / (size_t)T.ntrees);
+    const long long s = plan[si].s;
+    const long long qsin = s * c_qsin[slot], qcos = s * c_qcos[slot];     // :159-160
+    const int8_t* cd = T.codes + (size_t)t * 256 + 4 * idx;
+    const long long k0 = cd[0], k1 = cd[1], k2 = cd[2], k3 = cd[3];
+    RotNode n;
+    n.dr1 = (int16_t)((qcos * k0 - qsin * k1) >> 16);
+    n.dc1 = (int16_t)((qsin * k0 + qcos * k1) >> 16);
+    n.dr2 = (int16_t)((qcos * k2 - qsin * k3) >> 16);
+    n.dc2 = (int16_t)((qsin * k2 + qcos * k3) >> 16);
+    out[i] = n;
+  }
+}
+
+void launch_rot_table(const FaceTables& T, const ScaleEntry* plan, int nscales, int slot, RotNode* out, int grid, cudaStream_t st) {
+  rot_table_kernel<<<grid, 256, 0, st>>>(T, plan, nscales, slot, out);
 }
 
 }  // namespace pigo

@@ -2,6 +2,8 @@
 // (SURVEY.md section 8f, row N2).  Pure streaming: 4 bytes in, 1 byte out per pixel => HBM-bound (5 B/pixel);
 // 16 pixels per thread (4 x 16-byte loads, one 16-byte store), float64 arithmetic in the reference's operation order
 // (the library is built with -fmad=false).
+#include <algorithm>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -36,6 +38,45 @@ __global__ void __launch_bounds__(256) gray_kernel(const uint32_t* __restrict__ 
 void launch_gray(const uint8_t* rgba, size_t npix, uint8_t* gray, int grid, cudaStream_t st) {
   const int vec_ok = (((uintptr_t)rgba) % 16 == 0) && (((uintptr_t)gray) % 16 == 0);
   gray_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(rgba), npix, gray, vec_ok);
+}
+
+// ---- ImgToNRGBA for *image.YCbCr (core/image.go:60-76): section 8f row N3 ---------------------------------------------------
+// The reference calls color.YCbCrToRGB (Go standard library, image/color/ycbcr.go, go1.22 per go.mod:3 -- not under the
+// reference tree), restated here: JFIF conversion in 16.16 fixed point,
+//   yy1 = y * 0x10101;  r = yy1 + 91881*cr1;  g = yy1 - 22554*cb1 - 46802*cr1;  b = yy1 + 116130*cb1   (cb1 = cb-128, cr1 = cr-128)
+// each then clamped: a value whose bits 24..31 are all zero is shifted right by 16, anything else saturates to 0 (negative)
+// or 255.  The constants are the ones the reference's own test restates (core/image_test.go:118-138, which rounds instead
+// and therefore allows +-1); alpha is 0xff.  Chroma sample of pixel (x, y): image.YCbCr.COffset for the six subsample ratios,
+// relative to the rectangle origin (min_x, min_y) like image.go:66-67.
+// `gray` (optional) fuses RgbToGrayscale (core/grayscale.go:8-23) of the converted pixel, so the NRGBA image never has to
+// make the round trip through HBM when only the detector's input is wanted.
+__device__ __forceinline__ uint32_t sat16(int v) { return (uint32_t)v & 0xff000000u ? (uint32_t)(~(v >> 31)) & 0xffu : (uint32_t)(v >> 16); }
+
+__global__ void __launch_bounds__(256) ycbcr_kernel(const uint8_t* __restrict__ yp, const uint8_t* __restrict__ cbp, const uint8_t* __restrict__ crp,
+                                                    int y_stride, int c_stride, int sub, int min_x, int min_y, int width, int height,
+                                                    uint32_t* __restrict__ nrgba, uint8_t* __restrict__ gray) {
+  const size_t npix = (size_t)width * height;
+  const int xs = (sub == 1 || sub == 2) ? 1 : ((sub == 4 || sub == 5) ? 2 : 0);   // chroma x shift: 422/420 halve, 411/410 quarter
+  const int ys = (sub == 2 || sub == 3 || sub == 5) ? 1 : 0;                       // chroma y shift: 420/440/410 halve
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const int dy = (int)(i / width), dx = (int)(i - (size_t)dy * width);
+    const int sx = min_x + dx, sy = min_y + dy;                                   // image.go:66-67
+    const size_t siy = (size_t)dy * y_stride + dx;                                // YOffset: (y-Rect.Min.Y)*YStride + (x-Rect.Min.X)
+    const size_t sic = (size_t)((sy >> ys) - (min_y >> ys)) * c_stride + ((sx >> xs) - (min_x >> xs));   // COffset
+    const int yy1 = (int)__ldg(yp + siy) * 0x10101, cb1 = (int)__ldg(cbp + sic) - 128, cr1 = (int)__ldg(crp + sic) - 128;
+    const uint32_t r = sat16(yy1 + 91881 * cr1), gg = sat16(yy1 - 22554 * cb1 - 46802 * cr1), b = sat16(yy1 + 116130 * cb1);
+    const uint32_t px = r | (gg << 8) | (b << 16) | 0xff000000u;
+    if (nrgba) nrgba[i] = px;
+    if (gray) gray[i] = (uint8_t)luma(px);
+  }
+}
+
+void launch_ycbcr(const uint8_t* y, const uint8_t* cb, const uint8_t* cr, int y_stride, int c_stride, int subsample, int min_x, int min_y,
+                  int width, int height, uint8_t* nrgba, uint8_t* gray, int grid, cudaStream_t st) {
+  const size_t npix = (size_t)width * height;
+  const size_t want = (npix + 255) / 256;
+  ycbcr_kernel<<<(int)std::max<size_t>(1, std::min<size_t>(want, (size_t)grid)), 256, 0, st>>>(y, cb, cr, y_stride, c_stride, subsample, min_x, min_y, width,
+                                                                                             height, reinterpret_cast<uint32_t*>(nrgba), gray);
 }
 
 }  // namespace pigo

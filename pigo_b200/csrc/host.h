@@ -16,7 +16,7 @@ extern std::atomic<long long> g_launches;
 
 // Per-kernel CUDA-event timing (enabled by option "timing"): every launch of kernel class `slot` is bracketed by an
 // event pair on its stream; "t_<name>_ns" / "t_<name>_n" return the summed device time and the launch count.
-enum TimeSlot { T_TILED = 0, T_GATHER, T_DEEP, T_FINALIZE, T_CLUSTER, T_PUPLOC, T_GRAY, T_NSLOTS };
+enum TimeSlot { T_TILED = 0, T_GATHER, T_DEEP, T_FINALIZE, T_CLUSTER, T_PUPLOC, T_GRAY, T_SEEDS, T_ROTTAB, T_YCBCR, T_NSLOTS };
 void timing_reset();
 long long timing_query(const std::string& key);
 void timing_begin(int slot, cudaStream_t st);
@@ -38,8 +38,12 @@ struct Options {
   std::atomic<long long> tile_min_core_steps{3};   // ... and at least this many window steps of its largest scale
   std::atomic<long long> tile_prefetch{0};  // tile warps: child-pair prefetch (64-bit node loads) vs plain 32-bit node loads
   std::atomic<long long> gather_block{0};   // gather block edge in windows: 16, 8, or 0 = auto (8 for <= 4 frames)
-  std::atomic<long long> deep_group{8};     // lanes (trees per step) per window in the deep kernel: 8, 16 or 32
-  std::atomic<long long> sub_batch{0};      // frames per pipeline group (0 = auto: 128 for resident frames, 64 for host frames)
+  std::atomic<long long> deep_group{0};     // lanes (trees per step) per window in the deep kernel: 8, 16, 32; 0 = auto (32 for <= 4 frames: latency, else 8)
+  std::atomic<long long> sub_batch{0};      // frames per pipeline group (0 = auto: 128 for resident frames; host frames: see host_first)
+  std::atomic<long long> host_first{16};    // host frames, sub_batch=0: group sizes ramp f, 3f, 4f, 8f, 8f.. (f = host_first, groups <= 128) so that the
+                                            // first H2D copy that nothing can hide is short; 0 = uniform 64-frame groups
+  std::atomic<long long> rot_mode{0};       // rotated scan: 0 = table-driven block kernel + deep kernel, 1 = universal gather kernel
+  std::atomic<long long> puploc_mode{0};    // RunDetector kernel: 0 = (perturbation, tree)-pair kernel, 1 = warp-per-perturbation kernel
   std::atomic<long long> lanes{1};          // internal streams the groups alternate between
   std::atomic<long long> tile_tail_min{6};  // tail policy threshold
   std::atomic<long long> tile_band_ratio{200};  // a band spans scales up to ratio/100 x its first scale
@@ -54,7 +58,8 @@ struct Options {
         {"tile_min_core_steps", &Options::tile_min_core_steps}, {"tile_prefetch", &Options::tile_prefetch},
          {"gather_block", &Options::gather_block}, {"deep_group", &Options::deep_group},
         {"sub_batch", &Options::sub_batch}, {"lanes", &Options::lanes}, {"tile_tail_min", &Options::tile_tail_min},
-        {"tile_band_ratio", &Options::tile_band_ratio}, {"timing", &Options::timing}};
+        {"tile_band_ratio", &Options::tile_band_ratio}, {"timing", &Options::timing}, {"host_first", &Options::host_first},
+        {"rot_mode", &Options::rot_mode}, {"puploc_mode", &Options::puploc_mode}};
     for (const Entry& e : table)
       if (k == e.name) return &(this->*e.field);
     return nullptr;
@@ -81,6 +86,27 @@ struct PuplocTables {
   float scales;
 };
 
+// Work list of the (perturbation, tree)-pair RunDetector kernel (puploc.cu): work item w in [0, nwork) is the RunDetector
+// call of slot (w / span) * stride + first + w % span; position j = w % span selects the cascade tab[tab_of[j]] and the
+// flip flag flip_of[j] (or flipv[slot] when given).  All pointers are device pointers.
+constexpr int kMaxPupTabs = 12;
+struct PupWork {
+  const pigo_point* seeds;     // [slots]; perturbs < 0 marks an inactive slot
+  pigo_point* out;             // [slots]
+  const float* randoms;        // [slots][63][3] injected perturbation randoms, or nullptr (counter-based generator)
+  uint64_t rng_seed;
+  uint64_t slot_base;          // added to the slot index in the generator key (frame shards of one logical batch)
+  const uint8_t* frames;
+  size_t frame_stride;
+  const int32_t* slot_frame;   // frame of each slot (nullptr = frame 0) unless slots_per_frame > 0
+  const uint8_t* flipv;        // per-slot flip flags (nullptr: use flip_of[j])
+  int32_t slots_per_frame;     // > 0: frame = slot / slots_per_frame
+  int32_t nrows, ncols, dim, rot_slot;
+  int32_t first, span, stride, nwork, ntabs;
+  PuplocTables tab[kMaxPupTabs];
+  uint8_t tab_of[32], flip_of[32];
+};
+
 
 // ---- workspace -----------------------------------------------------------------------------------------
 struct DevBuf {
@@ -105,7 +131,8 @@ constexpr int kMaxLanes = 4;
 
 struct Workspace {
   cudaStream_t stream = nullptr;
-  DevBuf frames, raw, counters, out, nout, plan, tiles, scratch_a, scratch_b, scratch_c;
+  DevBuf frames, raw, counters, out, nout, plan, tiles, scratch_a, scratch_b, scratch_c, rot_tab;
+  int rot_slot = -1;                           // table slot the cached rotated node table was built for (-1 = none)
   DevBuf deep[kMaxLanes], longq[kMaxLanes];   // Q1 / Q2 per pipeline lane
   cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
@@ -152,7 +179,7 @@ struct Workspace {
     if (busy) cudaEventDestroy(busy);
     for (auto e : copy_events) cudaEventDestroy(e);
     if (copy_stream) cudaStreamDestroy(copy_stream);
-    tiles.release(); scratch_a.release(); scratch_b.release(); scratch_c.release();
+    tiles.release(); scratch_a.release(); scratch_b.release(); scratch_c.release(); rot_tab.release();
     if (pinned) cudaFreeHost(pinned);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -191,20 +218,49 @@ struct WsGuard {
 };
 
 
+// ---- devices -------------------------------------------------------------------------------------------
+// The library serves up to kMaxDevices GPUs from one process (single process, frames sharded over the
+// devices of a mask).  Handles keep the parsed tables on the host and build one device replica per GPU on first use.
+constexpr int kMaxDevices = 16;
+int use_device(int dev);        // validates (sm_100) + cudaSetDevice on the calling thread
+int default_device();           // device of the non-sharded entry points (pigo_init, implicit device 0)
+int device_sms(int dev);
+std::vector<int> shard_devices();   // devices of the mask given to pigo_init_devices, ascending
+
+struct FaceReplica {            // device copy of one face cascade
+  int device = 0, num_sms = 148;
+  DevBuf codes, preds, thresh, tiled_tab;
+  FaceTables tab{};
+  WorkspacePool pool;
+  ~FaceReplica() { cudaSetDevice(device); codes.release(); preds.release(); thresh.release(); tiled_tab.release(); }
+};
+struct PuplocReplica {
+  int device = 0, num_sms = 148;
+  DevBuf codes, preds;
+  PuplocTables tab{};
+  WorkspacePool pool;
+  ~PuplocReplica() { cudaSetDevice(device); codes.release(); preds.release(); }
+};
+
 }  // namespace pigo
 
 struct pigo_cascade {
   uint32_t depth = 0, ntrees = 0, leaves = 0;
-  pigo::DevBuf codes, preds, thresh, tiled_tab;
-  pigo::FaceTables tab{};
-  pigo::WorkspacePool pool;
-  int device = 0;
+  std::vector<int8_t> h_codes;          // reference layout (core/pigo.go:79-86), see FaceTables
+  std::vector<float> h_preds, h_thr;
+  std::mutex mu;
+  pigo::FaceReplica* rep[pigo::kMaxDevices] = {};
+  ~pigo_cascade() { for (auto* r : rep) delete r; }
 };
 
 struct pigo_puploc {
-  pigo::PuplocTables tab{};
-  pigo::DevBuf codes, preds;
-  pigo::WorkspacePool pool;
+  uint32_t stages = 0, trees = 0, depth = 0, leaves = 0;
+  float scales = 0.f;
+  std::vector<int8_t> h_codes;
+  std::vector<float> h_preds;
+  std::mutex mu;
+  pigo::PuplocReplica* rep[pigo::kMaxDevices] = {};
+  ~pigo_puploc() { for (auto* r : rep) delete r; }
 };
 
 
@@ -214,8 +270,11 @@ void launch_scan_gather(const ScanArgs& A, int grid, int max_scale, cudaStream_t
 void launch_scan_tiled(const TiledArgs& A, int grid, int threads, size_t smem, int ni, cudaStream_t st);
 int tiled_max_threads(int ni);
 void launch_gray(const uint8_t* rgba, size_t npix, uint8_t* gray, int grid, cudaStream_t st);
+void launch_ycbcr(const uint8_t* y, const uint8_t* cb, const uint8_t* cr, int y_stride, int c_stride, int subsample, int min_x, int min_y,
+                  int width, int height, uint8_t* nrgba, uint8_t* gray, int grid, cudaStream_t st);
 void launch_scan_gather2(const TiledArgs& A, int grid, size_t smem, cudaStream_t st);
-int gather2_ctas_per_sm(size_t smem, int ng);
+int gather2_ctas_per_sm(size_t smem, int ng, bool rot);
+void launch_rot_table(const FaceTables& T, const ScaleEntry* plan, int nscales, int slot, RotNode* out, int grid, cudaStream_t st);
 void launch_deep(const ScanArgs& A, unsigned long long* counter, int grid, int group, cudaStream_t st);
 int gather_max_ctas_per_sm(int depth, bool rot);
 void launch_finalize(const RawDet* raw, const int32_t* raw_count, int cap, const ScaleEntry* plan, int nscales, pigo_det* out,
@@ -225,8 +284,14 @@ void launch_cluster(pigo_det* dets, const int32_t* n_in, int cap, double thr, pi
 void launch_puploc(const PuplocTables& T, const pigo_point* seeds, int nseeds, const float* randoms, uint64_t rng_seed,
                    const uint8_t* frames, const int32_t* seed_frame, size_t frame_stride, int rows, int cols, int dim, int rot_slot,
                    const uint8_t* flipv, pigo_point* out, cudaStream_t st);
+int launch_puploc_pairs(const PupWork& W, unsigned int* counter, int num_sms, cudaStream_t st);
+void launch_eye_seeds(const pigo_det* clusters, const int32_t* ncl, int cl_cap, int nframes, int face_cap, int stride, int min_face,
+                      int eye_perturbs, pigo_det* faces, int32_t* nfaces, pigo_point* seeds, cudaStream_t st);
+void launch_landmark_seeds(const pigo_point* points, pigo_point* seeds, int nslots, int stride, int ncalls, int flp_perturbs, cudaStream_t st);
 int build_tiled_tables(const FaceTables& tab, const std::vector<int8_t>& codes, const std::vector<float>& preds,
                        const std::vector<float>& thr, DevBuf& out);
 int describe_plan(const std::vector<ScaleEntry>& plan, uint64_t wins, int ntrees, char* buf, size_t cap);
-int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long long* d_work, cudaStream_t st, int num_sms);
+int run_scan(FaceReplica* c, Workspace* w, int lane, ScanArgs& A, unsigned long long* d_work, cudaStream_t st, int num_sms);
+FaceReplica* face_replica(pigo_cascade* c, int dev, int* rc);
+PuplocReplica* puploc_replica(pigo_puploc* p, int dev, int* rc);
 }  // namespace pigo

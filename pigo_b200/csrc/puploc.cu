@@ -142,6 +142,226 @@ __global__ void __launch_bounds__(1024, 1) puploc_kernel(PuplocTables T, const p
   }
 }
 
+// ============================================================================================================
+// Round 2 kernel: (perturbation, tree) PAIRS.  The trees of a stage are independent of each other and so are the
+// perturbations, so a stage of one RunDetector call is P x trees independent tree walks (63 x 20 = 1260 for a landmark
+// call): they are dealt to the threads of the CTA as a flat list -- every lane walks a real tree (the warp-per-perturbation
+// kernel above keeps 20 of 32 lanes busy) -- the leaves go to shared memory, and one thread per perturbation forms the
+// float32 sums dr, dc in TREE ORDER exactly like the reference's sequential loop (core/puploc.go:138-151).
+// CTAs are persistent and pull work items (one RunDetector call each) from a global counter; an item is addressed as
+// slot = (w / span) * stride + first + w % span, which lets one launch cover e.g. "the two eye seeds of every face slot"
+// or "the 15 landmark calls of every face slot", each position j = w % span with its own cascade and flip flag.
+// Inactive slots (seed.perturbs < 0) are skipped.  32-bit coordinate arithmetic, exact because
+//   (256*int(r) + code*rs) >> 8  ==  int(r) + ((code*rs) >> 8)        (256*int(r) is a multiple of 256), and
+//   max(0, 65536*int(r) + x) >> 16  ==  max(0, int(r) + (x >> 16))    (rotated variant, see RotNode in common.cuh);
+// seeds with |Scale| > 16384 (products would leave 32 bits) are left to the 64-bit kernel above by the host.
+constexpr int kPairThreads = 512;
+// int(r) of core/puploc.go:118, kept inside +-2^30 so that adding a sample offset (|offset| <= |scale|/2 < 2^23, the host
+// rejects larger scales) cannot wrap: anything beyond +-2^30 clamps to the same image border as the exact value would
+__device__ __forceinline__ int clamp_coord(float v) { return max(-(1 << 30), min(1 << 30, (int)v)); }
+
+__global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupWork W, unsigned int* __restrict__ counter) {
+  extern __shared__ float2 s_leaf[];     // [63][trees]
+  __shared__ float s_r[64], s_c[64], s_s[64];
+  __shared__ int s_ir[64], s_ic[64], s_rs[64], s_qs[64], s_qc[64];
+  __shared__ unsigned s_item;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(counter, 1u);
+    __syncthreads();
+    const unsigned w = s_item;
+    if (w >= (unsigned)W.nwork) break;
+    const int j = (int)(w % (unsigned)W.span);
+    const int slot = (int)(w / (unsigned)W.span) * W.stride + W.first + j;
+    const pigo_point seed = W.seeds[slot];
+    const int P = seed.perturbs;
+    if (P < 0) continue;                                   // inactive slot (CTA-uniform)
+    const PuplocTables T = W.tab[W.tab_of[j]];
+    const bool flip = W.flipv ? (W.flipv[slot] != 0) : (W.flip_of[j] != 0);
+    const int frame = W.slots_per_frame > 0 ? slot / W.slots_per_frame : (W.slot_frame ? W.slot_frame[slot] : 0);
+    const uint8_t* __restrict__ pixels = W.frames + (size_t)frame * W.frame_stride;
+    const int L = T.leaves, tree_codes = 4 * L - 4, rlim = W.nrows - 1, clim = W.ncols - 1;
+    const bool rot = W.rot_slot >= 0;
+
+    if (tid < 64) {
+      float r = 0.f, c = 0.f, s = 0.f;
+      int qs = 0, qc = 0;
+      if (tid < P && tid < 63) {
+        float u0, u1, u2;
+        if (W.randoms) {
+          const float* rr = W.randoms + ((size_t)slot * 63 + tid) * 3;
+          u0 = rr[0]; u1 = rr[1]; u2 = rr[2];
+        } else {
+          const uint64_t key = W.rng_seed * 0xD1342543DE82EF95ull + ((uint64_t)slot + W.slot_base) * 64 + tid;
+          u0 = mix64(key * 3 + 0) * (1.0f / 16777216.0f);
+          u1 = mix64(key * 3 + 1) * (1.0f / 16777216.0f);
+          u2 = mix64(key * 3 + 2) * (1.0f / 16777216.0f);
+        }
+        const float t1 = __fmul_rn(seed.scale, 0.15f);
+        r = __fadd_rn((float)seed.row, __fmul_rn(t1, __fsub_rn(0.5f, u0)));   // core/puploc.go:248
+        c = __fadd_rn((float)seed.col, __fmul_rn(t1, __fsub_rn(0.5f, u1)));   // :249
+        s = __fmul_rn(seed.scale, __fadd_rn(0.925f, __fmul_rn(0.15f, u2)));   // :250
+        if (rot) {
+          qs = (int)__fmul_rn(s, c_qsinf[W.rot_slot]);     // int(qsin), :166,:188 (from the INITIAL s)
+          qc = (int)__fmul_rn(s, c_qcosf[W.rot_slot]);
+        }
+      }
+      s_r[tid] = r; s_c[tid] = c; s_s[tid] = s; s_qs[tid] = qs; s_qc[tid] = qc;
+      s_ir[tid] = clamp_coord(r); s_ic[tid] = clamp_coord(c); s_rs[tid] = (int)llround((double)s);   // int(r), int(math.Round(float64(s)))
+    }
+    __syncthreads();
+
+    const int npairs = P * T.trees;
+    for (int st = 0; st < T.stages; ++st) {
+      for (int p = tid; p < npairs; p += nt) {
+        const int i = p / T.trees, t = p - i * T.trees;
+        const int ir = s_ir[i], ic = s_ic[i], rs = s_rs[i];
+        const size_t tg = (size_t)st * T.trees + t;
+        const int* tc = reinterpret_cast<const int*>(T.codes + tg * tree_codes);      // tree_codes % 4 == 0
+        const float2* tp = reinterpret_cast<const float2*>(T.preds + tg * 2 * L);
+        int idx = 0;
+        int cw = __ldg(tc);
+        if (!rot) {
+          for (int k = 0; k < T.depth; ++k) {
+            // children of node idx are nodes 2idx+1, 2idx+2: fetched while this node's pixels are in flight
+            int kl = 0, kr = 0;
+            if (k + 1 < T.depth) { kl = __ldg(tc + 2 * idx + 1); kr = __ldg(tc + 2 * idx + 2); }
+            const int k0 = (int8_t)(cw), k2 = (int8_t)(cw >> 16);
+            const int k1 = flip ? neg_i8((int8_t)(cw >> 8)) : (int)(int8_t)(cw >> 8);
+            const int k3 = flip ? neg_i8(cw >> 24) : (cw >> 24);
+            const int r1 = __vimin_s32_relu(ir + ((k0 * rs) >> 8), rlim), r2 = __vimin_s32_relu(ir + ((k2 * rs) >> 8), rlim);   // :118-119
+            const int c1 = __vimin_s32_relu(ic + ((k1 * rs) >> 8), clim), c2 = __vimin_s32_relu(ic + ((k3 * rs) >> 8), clim);   // :124/:127
+            const int bit = __ldg(pixels + (size_t)r1 * W.dim + c1) > __ldg(pixels + (size_t)r2 * W.dim + c2) ? 1 : 0;          // :130-136
+            cw = bit ? kr : kl;
+            idx = 2 * idx + 1 + bit;
+          }
+        } else {
+          const long long iqs = s_qs[i], iqc = s_qc[i];        // 64-bit products: int(256*s)*code leaves 32 bits for s > 2^15
+          for (int k = 0; k < T.depth; ++k) {
+            int kl = 0, kr = 0;
+            if (k + 1 < T.depth) { kl = __ldg(tc + 2 * idx + 1); kr = __ldg(tc + 2 * idx + 2); }
+            const int k0 = (int8_t)(cw), k2 = (int8_t)(cw >> 16);
+            const int k1 = flip ? neg_i8((int8_t)(cw >> 8)) : (int)(int8_t)(cw >> 8);
+            const int k3 = flip ? neg_i8(cw >> 24) : (cw >> 24);
+            const int r1 = __vimin_s32_relu(ir + (int)((iqc * k0 - iqs * k1) >> 16), rlim);   // :188
+            const int c1 = __vimin_s32_relu(ic + (int)((iqs * k0 + iqc * k1) >> 16), clim);   // :189
+            const int r2 = __vimin_s32_relu(ir + (int)((iqc * k2 - iqs * k3) >> 16), rlim);   // :190
+            const int c2 = __vimin_s32_relu(ic + (int)((iqs * k2 + iqc * k3) >> 16), clim);   // :191
+            const int bit = __ldg(pixels + (size_t)r1 * W.dim + c1) <= __ldg(pixels + (size_t)r2 * W.dim + c2) ? 1 : 0;  // :193-199
+            cw = bit ? kr : kl;
+            idx = 2 * idx + 1 + bit;
+          }
+        }
+        s_leaf[p] = __ldg(tp + (idx - (L - 1)));
+      }
+      __syncthreads();
+      if (tid < P) {
+        float dr = 0.f, dc = 0.f;
+        const float2* lf = s_leaf + tid * T.trees;
+        for (int t = 0; t < T.trees; ++t) {                  // the reference's tree-ordered float32 sums, :140-145
+          dr = __fadd_rn(dr, lf[t].x);
+          dc = __fadd_rn(dc, flip ? -lf[t].y : lf[t].y);
+        }
+        const float s = s_s[tid];
+        const float r = __fadd_rn(s_r[tid], __fmul_rn(dr, s));   // :149
+        const float c = __fadd_rn(s_c[tid], __fmul_rn(dc, s));   // :150
+        const float s2 = __fmul_rn(s, T.scales);                 // :151
+        s_r[tid] = r; s_c[tid] = c; s_s[tid] = s2;
+        s_ir[tid] = clamp_coord(r); s_ic[tid] = clamp_coord(c); s_rs[tid] = (int)llround((double)s2);
+      }
+      __syncthreads();
+    }
+    // pool slots >= Perturbs stay 0 (fresh pool object, :228-236); all 63 slots are sorted (:267-269)
+    if (tid < 63) {
+      const int mid = (int)llround((double)P / 2);   // int(math.Round(float64(Perturbs)/2)), :273
+      const float vr = s_r[tid], vc = s_c[tid], vs = s_s[tid];
+      int kr = 0, kc = 0, ks = 0;
+      for (int q = 0; q < 63; ++q) {
+        kr += (s_r[q] < vr || (s_r[q] == vr && q < tid)) ? 1 : 0;
+        kc += (s_c[q] < vc || (s_c[q] == vc && q < tid)) ? 1 : 0;
+        ks += (s_s[q] < vs || (s_s[q] == vs && q < tid)) ? 1 : 0;
+      }
+      if (kr == mid) W.out[slot].row = (int)vr;      // int() truncation, :273
+      if (kc == mid) W.out[slot].col = (int)vc;
+      if (ks == mid) W.out[slot].scale = vs;
+      if (tid == 0) W.out[slot].perturbs = 0;        // the returned Puploc leaves Perturbs unset (:272-276)
+    }
+  }
+}
+
+int launch_puploc_pairs(const PupWork& W, unsigned int* counter, int num_sms, cudaStream_t st) {
+  int trees_max = 0;
+  for (int i = 0; i < W.ntabs; ++i) trees_max = max(trees_max, W.tab[i].trees);
+  const size_t smem = (size_t)63 * trees_max * sizeof(float2);
+  if (smem > 160 * 1024) return -1;                                   // caller falls back to the warp-per-perturbation kernel
+  static bool attr_set[kMaxDevices] = {};
+  int dev = 0; cudaGetDevice(&dev);
+  if (smem > 48 * 1024 && !attr_set[dev]) {
+    cudaFuncSetAttribute(puploc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_set[dev] = true;
+  }
+  const int grid = max(1, min(W.nwork, num_sms * 3));
+  puploc_pair_kernel<<<grid, kPairThreads, smem, st>>>(W, counter);
+  return 0;
+}
+
+// ---- seeds of the face -> pupils -> landmarks sequence (the CALLER's arithmetic in the reference) -----------------------
+// Eye seeds, core/flploc_test.go:103-118 == cmd/pigo/main.go:416-449 (float32 products, int() truncation):
+//   Row = face.Row - int(0.075*float32(Scale)); Col = face.Col -/+ int(0.175|0.185*float32(Scale)); Scale = float32(Scale)*0.25
+// One thread per (frame, face slot k).  Face slot layout: [frame][face_cap][stride], stride = 2 + ncalls.
+__global__ void __launch_bounds__(256) eye_seed_kernel(const pigo_det* __restrict__ clusters, const int32_t* __restrict__ ncl, int cl_cap,
+                                                       int nframes, int face_cap, int stride, int min_face, int eye_perturbs,
+                                                       pigo_det* __restrict__ faces, int32_t* __restrict__ nfaces, pigo_point* __restrict__ seeds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nframes * face_cap) return;
+  const int f = i / face_cap, k = i - f * face_cap;
+  const int n = ncl[f];
+  if (k == 0) nfaces[f] = n;                              // required count (may exceed face_cap: the caller retries)
+  pigo_point* sd = seeds + (size_t)i * stride;
+  const pigo_point off = {0, 0, 0.f, -1};
+  for (int j = 0; j < stride; ++j) sd[j] = off;
+  pigo_det d = {0, 0, 0, 0.f};
+  if (k < n && k < cl_cap) {
+    d = clusters[(size_t)f * cl_cap + k];
+    if (d.scale > min_face) {                             // core/flploc_test.go:102, cmd/pigo/main.go:404
+      const float fs = (float)d.scale;
+      const int row = d.row - (int)__fmul_rn(0.075f, fs);
+      sd[0] = pigo_point{row, d.col - (int)__fmul_rn(0.175f, fs), __fmul_rn(fs, 0.25f), eye_perturbs};
+      sd[1] = pigo_point{row, d.col + (int)__fmul_rn(0.185f, fs), __fmul_rn(fs, 0.25f), eye_perturbs};
+    }
+  }
+  faces[i] = d;
+}
+
+// Landmark seeds, GetLandmarkPoint core/flploc.go:37-50 (float64): one thread per (face slot, call).
+__global__ void __launch_bounds__(256) landmark_seed_kernel(const pigo_point* __restrict__ points, pigo_point* __restrict__ seeds, int nslots,
+                                                            int stride, int ncalls, int flp_perturbs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nslots * ncalls) return;
+  const int fs = i / ncalls, cidx = i - fs * ncalls;
+  const size_t base = (size_t)fs * stride;
+  if (seeds[base].perturbs < 0) return;                   // face without eye seeds
+  const pigo_point le = points[base], re = points[base + 1];
+  const long long dx = (long long)(le.row - re.row) * (le.row - re.row);
+  const long long dy = (long long)(le.col - re.col) * (le.col - re.col);
+  const double dist = __dsqrt_rn((double)(dx + dy));
+  const double row = __dadd_rn((double)(le.row + re.row) / 2.0, __dmul_rn(0.25, dist));
+  const double col = __dadd_rn((double)(le.col + re.col) / 2.0, __dmul_rn(0.15, dist));
+  seeds[base + 2 + cidx] = pigo_point{(int)row, (int)col, (float)__dmul_rn(3.0, dist), flp_perturbs};
+}
+
+void launch_eye_seeds(const pigo_det* clusters, const int32_t* ncl, int cl_cap, int nframes, int face_cap, int stride, int min_face,
+                      int eye_perturbs, pigo_det* faces, int32_t* nfaces, pigo_point* seeds, cudaStream_t st) {
+  const int n = nframes * face_cap;
+  eye_seed_kernel<<<(n + 255) / 256, 256, 0, st>>>(clusters, ncl, cl_cap, nframes, face_cap, stride, min_face, eye_perturbs, faces, nfaces, seeds);
+}
+void launch_landmark_seeds(const pigo_point* points, pigo_point* seeds, int nslots, int stride, int ncalls, int flp_perturbs, cudaStream_t st) {
+  const int n = nslots * ncalls;
+  if (n <= 0) return;
+  landmark_seed_kernel<<<(n + 255) / 256, 256, 0, st>>>(points, seeds, nslots, stride, ncalls, flp_perturbs);
+}
+
 void launch_puploc(const PuplocTables& T, const pigo_point* seeds, int nseeds, const float* randoms, uint64_t rng_seed,
                    const uint8_t* frames, const int32_t* seed_frame, size_t frame_stride, int rows, int cols, int dim, int rot_slot,
                    const uint8_t* flipv, pigo_point* out, cudaStream_t st) {

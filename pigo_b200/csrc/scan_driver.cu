@@ -194,7 +194,7 @@ static int check_launch(const char* what) {
   return PIGO_OK;
 }
 
-int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long long* d_work, cudaStream_t st, int num_sms) {
+int run_scan(FaceReplica* c, Workspace* w, int lane, ScanArgs& A, unsigned long long* d_work, cudaStream_t st, int num_sms) {
   int rc;
   const bool rot = A.rot_slot >= 0;
   const long long mode = g_opt.scan_mode.load();
@@ -205,9 +205,14 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
   A.chunk = (uint32_t)std::max<long long>(32, g_opt.chunk.load());
   A.chunk_counter = d_work + 6;
 
-  const bool fast = !rot && A.tab.depth == 6 && c->tiled_tab.p != nullptr && mode != 1;
+  // Rotated scan on the block/deep structure: needs the per-call node table (one RotNode per ladder entry, tree, node).
+  const size_t rot_bytes = (size_t)A.nscales * (size_t)A.tab.ntrees * 64 * sizeof(RotNode);
+  const int max_scale = w->plan_host.empty() ? 0 : w->plan_host.back().s;
+  const bool rot_fast = rot && A.tab.depth == 6 && c->tiled_tab.p != nullptr && mode != 1 && g_opt.rot_mode.load() == 0 &&
+                        max_scale <= 32000 && rot_bytes <= ((size_t)1 << 29);
+  const bool fast = (!rot || rot_fast) && A.tab.depth == 6 && c->tiled_tab.p != nullptr && mode != 1;
   if (!fast) {
-    // ---- universal path: standalone gather kernel over every scale (rotated path, other depths, scan_mode=1)
+    // ---- universal path: standalone gather kernel over every scale (any tree depth, scan_mode=1, rot_mode=1)
     ScanArgs G = A;
     G.scale_lo = 0; G.scale_hi = A.nscales;
     G.chunks_per_frame = (A.wins_per_frame + G.chunk - 1) / G.chunk;
@@ -215,10 +220,22 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
     const unsigned long long total_chunks = (unsigned long long)G.chunks_per_frame * A.nframes;
     const long long grid = std::max(1ll, std::min<long long>((long long)num_sms * per_sm, (long long)((total_chunks + 7) / 8)));
     timing_begin(T_GATHER, st);
-    launch_scan_gather(G, (int)grid, w->plan_host.empty() ? 0 : w->plan_host.back().s, st);
+    launch_scan_gather(G, (int)grid, max_scale, st);
     timing_end(T_GATHER, st);
     g_launches++;
     return check_launch("gather scan");
+  }
+  if (rot_fast) {
+    if (w->rot_slot != A.rot_slot || w->rot_tab.p == nullptr) {
+      if ((rc = w->rot_tab.reserve(rot_bytes))) return rc;
+      timing_begin(T_ROTTAB, st);
+      launch_rot_table(A.tab, A.plan, A.nscales, A.rot_slot, (RotNode*)w->rot_tab.p, num_sms * 8, st);
+      timing_end(T_ROTTAB, st);
+      g_launches++;
+      if ((rc = check_launch("rotated node table"))) return rc;
+      w->rot_slot = A.rot_slot;
+    }
+    A.rot_tab = (const RotNode*)w->rot_tab.p;
   }
 
   // ---- queues
@@ -241,7 +258,8 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
   T.tile_prefetch = g_opt.tile_prefetch.load() ? 1 : 0;
   T.gather_ni = (int)std::min<long long>(std::max<long long>(1, g_opt.gather_ni.load()), 3);
   // small batches (a frame or two) cannot fill the GPU with 256-window blocks: use 64-window blocks then
-  T.gb_shift = (g_opt.gather_block.load() == 8 || (g_opt.gather_block.load() == 0 && A.nframes <= 4)) ? 3 : 4;
+  // (decided from the frames of the whole API call, not of this pipeline group: the block prefix lives in the shared plan)
+  T.gb_shift = (g_opt.gather_block.load() == 8 || (g_opt.gather_block.load() == 0 && A.batch_frames <= 4)) ? 3 : 4;
 
   // ---- fused kernel: tile warps over the small scales (+ optional gather warps over the rest)
   auto round_ks = [&](long long v) {
@@ -250,7 +268,7 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
   };
   int first_untiled = 0;
   bool blocks_done = false, tiled_ran = false;
-  if (mode != 3) {
+  if (mode != 3 && !rot) {
     FusedPlan P = plan_fused(w->plan_host, A.tab.ntrees);
     const TilePlan& tp = P.tp;
     const int W = P.W;
@@ -298,7 +316,8 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
     if (G.consume_q1 || G.gather_blocks_per_frame > 0) {
       const size_t smem = ((384 + (size_t)G.ks * kTreeRec + 127) & ~(size_t)127);
       int per_sm = (int)g_opt.gather_ctas_per_sm.load();
-      const int occ = gather2_ctas_per_sm(smem, G.gather_ni);
+      if (rot) G.gather_ni = std::min(G.gather_ni, 2);
+      const int occ = gather2_ctas_per_sm(smem, G.gather_ni, rot);
       if (per_sm <= 0 || per_sm > occ) per_sm = occ;
       timing_begin(T_GATHER, st);
       launch_scan_gather2(G, num_sms * per_sm, smem, st);
@@ -311,7 +330,9 @@ int run_scan(pigo_cascade* c, Workspace* w, int lane, ScanArgs& A, unsigned long
   // ---- deep kernel: Q2, one warp per window, 32 trees per step
   {
     timing_begin(T_DEEP, st);
-    launch_deep(A, d_work + 3, num_sms * 8, (int)g_opt.deep_group.load(), st);
+    int group = (int)g_opt.deep_group.load();
+    if (group != 8 && group != 16 && group != 32) group = A.batch_frames <= 4 ? 32 : 8;   // few frames: latency of a full survivor matters
+    launch_deep(A, d_work + 3, num_sms * 8, group, st);
     timing_end(T_DEEP, st);
     g_launches++;
     if ((rc = check_launch("deep scan"))) return rc;

@@ -70,7 +70,28 @@ __device__ __forceinline__ int sx3(int w) { return w >> 24; }
 // as scan_gather_kernel, but (a) node codes / leaves / thresholds of the first KS trees come from the shared-memory
 // cascade prefix, and (b) work is handed out as 2-D blocks of 16x16 windows of one scale, so that the pixels a
 // CTA touches stay L1-resident instead of streaming whole window rows through L2.
-template <int NG>
+// One tree of classifyRotatedRegion (core/pigo.go:164-180) with the node's four sample deltas read from the per-call table
+// (RotNode, common.cuh): `tn` = this (scale, tree)'s 64 node records.  Both children of a node are adjacent 8-byte records,
+// fetched with one 16-byte load while the node's two pixels are in flight.  Returns the final heap index (64..127).
+__device__ __forceinline__ int walk_rot_nodes(const RotNode* __restrict__ tn, const uint8_t* __restrict__ fb, int r, int c, int dim, int lim) {
+  uint2 cur = __ldg(reinterpret_cast<const uint2*>(tn + 1));
+  int idx = 1;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    uint4 kids = make_uint4(0, 0, 0, 0);
+    if (j < 5) kids = __ldg(reinterpret_cast<const uint4*>(tn + 2 * idx));
+    // min(nrows-1, max(0, .)) for rows AND columns: the reference's column clamp quirk (core/pigo.go:168,:171)
+    const int r1 = __vimin_s32_relu(r + (int)(short)(cur.x & 0xffff), lim), c1 = __vimin_s32_relu(c + ((int)cur.x >> 16), lim);
+    const int r2 = __vimin_s32_relu(r + (int)(short)(cur.y & 0xffff), lim), c2 = __vimin_s32_relu(c + ((int)cur.y >> 16), lim);
+    const unsigned p1 = __ldg(fb + (size_t)r1 * dim + c1), p2 = __ldg(fb + (size_t)r2 * dim + c2);
+    const bool right = p1 <= p2;                       // core/pigo.go:179
+    cur = right ? make_uint2(kids.z, kids.w) : make_uint2(kids.x, kids.y);
+    idx = 2 * idx + (right ? 1 : 0);
+  }
+  return idx;
+}
+
+template <int NG, int ROT>
 __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* smem, uint32_t casc, uint32_t casc_end) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -83,19 +104,22 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
   bool from_q1 = false;
   if (!blocks_more && !q1_more) return;
   const uint32_t tbo_last = casc + (uint32_t)T.ntrees * kTreeRec;   // record offset "one past the last tree"
+  const int lim = S.rows - 1;
 
   // NG independent windows per lane: their dependent LDS -> L2 gather chains overlap (ILP), which is what hides the
   // ~600-cycle L2 latency when only a few gather warps fit beside the tile warps.
+  // Per window: unrotated -- pc = centre pixel, sv = scale;  rotated -- pc = frame base, (wr, wc) = centre, sv = index of
+  // the (scale, tree) node table in S.rot_tab (units of 64 RotNode records; advances by one per tree).
   bool alive[NG];
   const uint8_t* pc[NG];
-  int sv[NG], fr[NG];
+  int sv[NG], fr[NG], wr[NG], wc[NG];
   uint32_t tbo[NG], wid[NG];
   float acc[NG];
 #pragma unroll
-  for (int u = 0; u < NG; ++u) { alive[u] = false; pc[u] = S.frames; sv[u] = 0; fr[u] = 0; tbo[u] = casc; wid[u] = 0; acc[u] = 0.f; }
+  for (int u = 0; u < NG; ++u) { alive[u] = false; pc[u] = S.frames; sv[u] = 0; fr[u] = 0; wr[u] = 0; wc[u] = 0; tbo[u] = casc; wid[u] = 0; acc[u] = 0.f; }
   // per-warp block cursor (uniform)
   uint32_t cur = 0, end = 0;
-  int b_s = 0, b_step = 0, b_r0 = 0, b_c0 = 0, b_w = 1, b_ncols = 0, cframe = 0;
+  int b_s = 0, b_step = 0, b_r0 = 0, b_c0 = 0, b_w = 1, b_ncols = 0, cframe = 0, b_si = 0;
   uint32_t b_wid0 = 0;
   bool more = true;
 
@@ -141,7 +165,7 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
           const uint32_t by = local / nbx, bx = local - by * nbx;
           b_w = min(GB, e.ncols - (int)(bx << gsh));
           const int b_h = min(GB, e.nrows - (int)(by << gsh));
-          b_s = e.s; b_step = e.step; b_ncols = e.ncols;
+          b_s = e.s; b_step = e.step; b_ncols = e.ncols; b_si = lo;
           b_r0 = e.off + (int)(by << gsh) * e.step;
           b_c0 = e.off + (int)(bx << gsh) * e.step;
           b_wid0 = e.wbase + (by << gsh) * (uint32_t)e.ncols + (bx << gsh);
@@ -158,16 +182,19 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
             const ScaleEntry e = S.plan[si];
             const uint32_t local = it.wid - e.wbase;
             const uint32_t ri = local / (uint32_t)e.ncols, ci = local - ri * (uint32_t)e.ncols;
-            wid[u] = it.wid; sv[u] = e.s; fr[u] = it.frame;
-            pc[u] = S.frames + (size_t)it.frame * S.frame_stride + (size_t)(e.off + (int)ri * e.step) * S.dim + (e.off + (int)ci * e.step);
+            wid[u] = it.wid; fr[u] = it.frame;
+            const int r = e.off + (int)ri * e.step, c = e.off + (int)ci * e.step;
+            if (ROT) { pc[u] = S.frames + (size_t)it.frame * S.frame_stride; wr[u] = r; wc[u] = c; sv[u] = si * T.ntrees + it.tree; }
+            else { pc[u] = S.frames + (size_t)it.frame * S.frame_stride + (size_t)r * S.dim + c; sv[u] = e.s; }
             tbo[u] = casc + (uint32_t)it.tree * kTreeRec; acc[u] = it.acc;
           } else {
             const uint32_t ly = b_w == (1 << A.gb_shift) ? (k >> A.gb_shift) : k / (uint32_t)b_w;
             const uint32_t lx = k - ly * (uint32_t)b_w;
             const int r = b_r0 + (int)ly * b_step, c = b_c0 + (int)lx * b_step;
             wid[u] = b_wid0 + ly * (uint32_t)b_ncols + lx;
-            sv[u] = b_s; fr[u] = cframe;
-            pc[u] = S.frames + (size_t)cframe * S.frame_stride + (size_t)r * S.dim + c;
+            fr[u] = cframe;
+            if (ROT) { pc[u] = S.frames + (size_t)cframe * S.frame_stride; wr[u] = r; wc[u] = c; sv[u] = b_si * T.ntrees; }
+            else { pc[u] = S.frames + (size_t)cframe * S.frame_stride + (size_t)r * S.dim + c; sv[u] = b_s; }
             tbo[u] = casc; acc[u] = 0.f;
           }
           alive[u] = true;
@@ -179,7 +206,8 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
     }
     if (!live_any) break;
 
-    // ---- one tree per live window; dead slots redo tree 0 at their last pixel with s = 0 (harmless)
+    // ---- one tree per live window; dead slots redo tree 0 (unrotated: at their last pixel with s = 0; rotated: the
+    //      first node table at their last centre) -- harmless, results ignored
     bool beyond = false;
 #pragma unroll
     for (int u = 0; u < NG; ++u) {
@@ -189,26 +217,31 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
     int idx[NG];
     float pred[NG], thr[NG];
     if (!__any_sync(FULL, beyond)) {
-      // plain walk: one 32-bit node load per level from the shared cascade prefix (the node load is ~30 cycles next to a
-      // ~600-cycle pixel gather, so prefetching it would only add shared-memory wavefronts to an L1TEX-bound kernel)
+      if (ROT) {
 #pragma unroll
-      for (int u = 0; u < NG; ++u) idx[u] = 1;
+        for (int u = 0; u < NG; ++u) idx[u] = walk_rot_nodes(S.rot_tab + (size_t)sv[u] * 64, pc[u], wr[u], wc[u], S.dim, lim);
+      } else {
+        // plain walk: one 32-bit node load per level from the shared cascade prefix (the node load is ~30 cycles next to a
+        // ~600-cycle pixel gather, so prefetching it would only add shared-memory wavefronts to an L1TEX-bound kernel)
 #pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        int cw[NG];
+        for (int u = 0; u < NG; ++u) idx[u] = 1;
 #pragma unroll
-        for (int u = 0; u < NG; ++u) cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4 * idx[u]);
-        unsigned p1[NG], p2[NG];
+        for (int j = 0; j < 6; ++j) {
+          int cw[NG];
 #pragma unroll
-        for (int u = 0; u < NG; ++u) {
-          const int s = sv[u];
-          const int o1 = ((sx0(cw[u]) * s) >> 8) * S.dim + ((sx1(cw[u]) * s) >> 8);
-          const int o2 = ((sx2(cw[u]) * s) >> 8) * S.dim + ((sx3(cw[u]) * s) >> 8);
-          p1[u] = __ldg(pc[u] + o1);
-          p2[u] = __ldg(pc[u] + o2);
+          for (int u = 0; u < NG; ++u) cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4 * idx[u]);
+          unsigned p1[NG], p2[NG];
+#pragma unroll
+          for (int u = 0; u < NG; ++u) {
+            const int s = sv[u];
+            const int o1 = ((sx0(cw[u]) * s) >> 8) * S.dim + ((sx1(cw[u]) * s) >> 8);
+            const int o2 = ((sx2(cw[u]) * s) >> 8) * S.dim + ((sx3(cw[u]) * s) >> 8);
+            p1[u] = __ldg(pc[u] + o1);
+            p2[u] = __ldg(pc[u] + o2);
+          }
+#pragma unroll
+          for (int u = 0; u < NG; ++u) idx[u] = 2 * idx[u] + (p1[u] <= p2[u] ? 1 : 0);
         }
-#pragma unroll
-        for (int u = 0; u < NG; ++u) idx[u] = 2 * idx[u] + (p1[u] <= p2[u] ? 1 : 0);
       }
 #pragma unroll
       for (int u = 0; u < NG; ++u) {
@@ -222,15 +255,19 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
       for (int u = 0; u < NG; ++u) {
         const bool res = tbo[u] < casc_end;
         const int tv = (int)((tbo[u] - casc) / kTreeRec);
-        const int* tc = reinterpret_cast<const int*>(T.codes + (size_t)tv * 256);
         int ix = 1;
-        const int s = sv[u];
-        for (int j = 0; j < 6; ++j) {
-          const int cw = res ? *reinterpret_cast<const int*>(smem + tbo[u] + 4 * ix) : __ldg(tc + ix);
-          const int o1 = ((sx0(cw) * s) >> 8) * S.dim + ((sx1(cw) * s) >> 8);
-          const int o2 = ((sx2(cw) * s) >> 8) * S.dim + ((sx3(cw) * s) >> 8);
-          const unsigned q1 = __ldg(pc[u] + o1), q2 = __ldg(pc[u] + o2);
-          ix = 2 * ix + (q1 <= q2 ? 1 : 0);
+        if (ROT) {
+          ix = walk_rot_nodes(S.rot_tab + (size_t)sv[u] * 64, pc[u], wr[u], wc[u], S.dim, lim);
+        } else {
+          const int* tc = reinterpret_cast<const int*>(T.codes + (size_t)tv * 256);
+          const int s = sv[u];
+          for (int j = 0; j < 6; ++j) {
+            const int cw = res ? *reinterpret_cast<const int*>(smem + tbo[u] + 4 * ix) : __ldg(tc + ix);
+            const int o1 = ((sx0(cw) * s) >> 8) * S.dim + ((sx1(cw) * s) >> 8);
+            const int o2 = ((sx2(cw) * s) >> 8) * S.dim + ((sx3(cw) * s) >> 8);
+            const unsigned q1 = __ldg(pc[u] + o1), q2 = __ldg(pc[u] + o2);
+            ix = 2 * ix + (q1 <= q2 ? 1 : 0);
+          }
         }
         idx[u] = ix;
         pred[u] = res ? *reinterpret_cast<const float*>(smem + tbo[u] + 4 * ix) : __ldg(T.preds + (size_t)tv * 64 + ix - 64);
@@ -242,6 +279,7 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
       if (alive[u]) {
         acc[u] += pred[u];                               // core/pigo.go:137
         tbo[u] += kTreeRec;
+        if (ROT) sv[u] += 1;                             // next tree's node table
         if (acc[u] <= thr[u]) {                          // :139-141
           alive[u] = false;
         } else if (tbo[u] == tbo_last) {
@@ -252,7 +290,7 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
           }
           alive[u] = false;
         } else if (tbo[u] >= casc_end && S.longq != nullptr) {
-          // survived the resident trees: hand over to the deep (32-trees-per-step) kernel; if its queue is full
+          // survived the resident trees: hand over to the deep (GROUP-trees-per-step) kernel; if its queue is full
           // the window simply continues here on the global tables
           const unsigned pos = atomicAdd(S.long_count, 1u);
           if (pos < S.long_cap) {
@@ -284,14 +322,14 @@ __device__ __forceinline__ void stage_cascade(const TiledArgs& A, uint32_t smem_
 
 // gather-v2: every warp plays the gather role (untiled scales in 16x16-window blocks + the Q1 stragglers), with the
 // cascade prefix in shared memory.  256 threads, several CTAs per SM.
-template <int NG, int MINB>
+template <int NG, int MINB, int ROT>
 __global__ void __launch_bounds__(256, MINB) scan_gather2_kernel(const TiledArgs A) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
   const uint32_t casc = kCascOff;
   const uint32_t casc_bytes = (uint32_t)A.ks * kTreeRec;
   stage_cascade(A, smem_base, casc, (casc_bytes + 15u) & ~15u);
-  gather_role<NG>(A, smem, casc, casc + casc_bytes);
+  gather_role<NG, ROT>(A, smem, casc, casc + casc_bytes);
 }
 
 template <int NI, int MAXT>
@@ -313,8 +351,8 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
 
   const ScanArgs& S = A.scan;
   if (warp >= A.tile_warps) {   // warp-specialised: the remaining warps scan the large scales by global-memory gathers
-    if (A.gather_ni >= 2) gather_role<2>(A, smem, casc, casc_end);
-    else gather_role<1>(A, smem, casc, casc_end);
+    if (A.gather_ni >= 2) gather_role<2, 0>(A, smem, casc, casc_end);
+    else gather_role<1, 0>(A, smem, casc, casc_end);
     return;
   }
   uint32_t tile_phase = 0;
@@ -618,20 +656,21 @@ static void launch_tiled_ni(const TiledArgs& A, int grid, int threads, size_t sm
   scan_tiled_kernel<NI, MAXT><<<grid, threads, smem, st>>>(A);
 }
 
-static const void* gather2_fn(int ng) {
-  if (ng >= 3) return (const void*)scan_gather2_kernel<3, 4>;
-  if (ng == 2) return (const void*)scan_gather2_kernel<2, 4>;
-  return (const void*)scan_gather2_kernel<1, 6>;
+static const void* gather2_fn(int ng, bool rot) {
+  if (rot) return ng >= 2 ? (const void*)scan_gather2_kernel<2, 4, 1> : (const void*)scan_gather2_kernel<1, 6, 1>;
+  if (ng >= 3) return (const void*)scan_gather2_kernel<3, 4, 0>;
+  if (ng == 2) return (const void*)scan_gather2_kernel<2, 4, 0>;
+  return (const void*)scan_gather2_kernel<1, 6, 0>;
 }
 void launch_scan_gather2(const TiledArgs& A, int grid, size_t smem, cudaStream_t st) {
-  const void* fn = gather2_fn(A.gather_ni);
+  const void* fn = gather2_fn(A.gather_ni, A.scan.rot_slot >= 0);
   cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   void* args[] = {(void*)&A};
   cudaLaunchKernel(fn, dim3(grid), dim3(256), args, smem, st);
 }
-int gather2_ctas_per_sm(size_t smem, int ng) {
+int gather2_ctas_per_sm(size_t smem, int ng, bool rot) {
   int n = 0;
-  const void* fn = gather2_fn(ng);
+  const void* fn = gather2_fn(ng, rot);
   cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, 256, smem) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
   return n;

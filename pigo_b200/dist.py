@@ -42,3 +42,24 @@ def merge_gathered(dets_list: List[torch.Tensor], counts_list: List[torch.Tensor
     d = torch.cat(dets_list, dim=0)[:nframes]
     c = torch.cat(counts_list, dim=0)[:nframes]
     return d, c
+
+
+def gather_pipeline(faces: torch.Tensor, nfaces: torch.Tensor, points: torch.Tensor, dst: int = 0, group=None):
+    """The gather of the full pipeline (BASELINE configs[4]): faces [n_local, cap, 4] int32, nfaces [n_local] int32 and
+    points [n_local, cap, 2 + ncalls, 4] int32 (eyes + landmark calls) of every rank's frame shard, to `dst`, in rank
+    (= frame) order.  Returns (faces_list, nfaces_list, points_list) on dst, None elsewhere."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        return [faces], [nfaces], [points]
+    outs = []
+    for t in (nfaces, faces, points):
+        lst = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+        dist.gather(t, lst, dst=dst, group=group)
+        outs.append(lst)
+    return (outs[1], outs[0], outs[2]) if rank == dst else None
+
+
+def merge_pipeline(faces_list, nfaces_list, points_list, nframes: int):
+    """Frame-ordered concatenation of the gathered shards, padding frames of the last shard dropped."""
+    return (torch.cat(faces_list, dim=0)[:nframes], torch.cat(nfaces_list, dim=0)[:nframes], torch.cat(points_list, dim=0)[:nframes])

@@ -104,3 +104,65 @@ def detect_batch(clf: Pigo, plc: PuplocCascade, flpcs: Dict[str, PuplocCascade],
         return out
     finally:
         df.free()
+
+
+# ---- the same sequence on the device: ONE library call, no host round trips (pigo_detect_batch) --------------------------
+def landmark_call_arrays(flpcs: Dict[str, PuplocCascade]):
+    """(handles[ncalls], flips[ncalls]) of the reference's 15-call landmark sequence (core/flploc_test.go:122-146)."""
+    import ctypes as C
+    calls = landmark_calls()
+    hs = (C.c_void_p * len(calls))(*[flpcs[n]._h.value if isinstance(flpcs[n]._h, C.c_void_p) else flpcs[n]._h for n, _ in calls])
+    fl = np.array([1 if f else 0 for _, f in calls], dtype=np.uint8)
+    return hs, fl
+
+
+def detect_batch_device(clf: Pigo, plc: PuplocCascade, flpcs: Dict[str, PuplocCascade], frames, cp: CascadeParams, iou: float = 0.1,
+                        min_face: int = 50, eye_perturbs: int = 50, flp_perturbs: int = 63, face_cap: int = 32, angle: float = 0.0,
+                        randoms: Optional[np.ndarray] = None, rng_seed: int = 0, sharded: bool = False, det_cap: int = 0,
+                        raw: bool = False):
+    """face -> cluster -> pupils -> 15 landmarks for a frame batch with the sequencing on the device.
+    frames: (N, Rows, Dim) uint8 host array, or a DeviceFrames.  randoms: optional [N][face_cap][17][63][3] float32.
+    Returns List[List[Face]] like detect_batch (raw=True: the (faces, n_faces, points) arrays)."""
+    import ctypes as C
+    from . import DET_DTYPE, POINT_DTYPE, FRAMES_DEVICE, MEM_HOST, PIGO_E_CAP, DeviceFrames, PipelineParams, _check, lib
+    hs, fl = landmark_call_arrays(flpcs)
+    ncalls = len(fl)
+    on_dev = isinstance(frames, DeviceFrames)
+    if on_dev:
+        nf, stride, fptr = frames.nframes, frames.stride, frames.ptr
+    else:
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        nf, stride, fptr = frames.shape[0], frames.strides[0], frames.ctypes.data
+    img = cp.ImageParams
+    prm = PipelineParams(cp.MinSize, cp.MaxSize, cp.ShiftFactor, cp.ScaleFactor, angle, iou, min_face, eye_perturbs, flp_perturbs, det_cap)
+    rnd = None
+    if randoms is not None:
+        rnd = np.ascontiguousarray(randoms, dtype=np.float32)
+        assert rnd.size == nf * face_cap * (2 + ncalls) * 189, "randoms must be [N][face_cap][2+ncalls][63][3]"
+    faces = np.zeros((nf, face_cap), dtype=DET_DTYPE)
+    nfaces = np.zeros(max(nf, 1), dtype=np.int32)
+    points = np.zeros((nf, face_cap, 2 + ncalls), dtype=POINT_DTYPE)
+    L = lib()
+    if sharded:
+        rc = L.pigo_detect_batch_sharded(clf._h, plc._h, hs, fl.ctypes.data, ncalls, fptr, nf, stride, img.Rows, img.Cols, img.Dim, C.byref(prm),
+                                         rnd.ctypes.data if rnd is not None else None, rng_seed, faces.ctypes.data, face_cap,
+                                         nfaces.ctypes.data, points.ctypes.data)
+    else:
+        rc = L.pigo_detect_batch(clf._h, plc._h, hs, fl.ctypes.data, ncalls, fptr, nf, stride, img.Rows, img.Cols, img.Dim, C.byref(prm),
+                                 rnd.ctypes.data if rnd is not None else None, rng_seed, faces.ctypes.data, face_cap, nfaces.ctypes.data,
+                                 points.ctypes.data, FRAMES_DEVICE if on_dev else MEM_HOST, None)
+    _check(rc)
+    if raw:
+        return faces, nfaces[:nf], points
+    out: List[List[Face]] = []
+    for f in range(nf):
+        fl_ = []
+        for k in range(int(nfaces[f])):
+            d = faces[f, k]
+            fc = Face((int(d["row"]), int(d["col"]), int(d["scale"]), float(d["q"])))
+            if d["scale"] > min_face:
+                pts = [Puploc(int(p["row"]), int(p["col"]), float(np.float32(p["scale"])), int(p["perturbs"])) for p in points[f, k]]
+                fc.left_eye, fc.right_eye, fc.landmarks = pts[0], pts[1], pts[2:]
+            fl_.append(fc)
+        out.append(fl_)
+    return out

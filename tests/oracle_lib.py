@@ -179,3 +179,25 @@ def rgba_to_gray(rgba: np.ndarray) -> np.ndarray:
     out = np.zeros(n, dtype=np.uint8)
     lib().oracle_rgba_to_gray(_ptr(rgba), n, _ptr(out))
     return out.reshape(rgba.shape[:-1])
+
+
+def ycbcr_to_nrgba(y, cb, cr, subsample, width, height, min_x=0, min_y=0) -> np.ndarray:
+    y = np.ascontiguousarray(y, dtype=np.uint8); cb = np.ascontiguousarray(cb, dtype=np.uint8); cr = np.ascontiguousarray(cr, dtype=np.uint8)
+    out = np.zeros((height, width, 4), dtype=np.uint8)
+    L = lib()
+    L.oracle_ycbcr_to_nrgba.argtypes = [C.c_void_p] * 3 + [C.c_int] * 7 + [C.c_void_p]
+    L.oracle_ycbcr_to_nrgba(_ptr(y), _ptr(cb), _ptr(cr), y.shape[1], cb.shape[1], subsample, min_x, min_y, width, height, _ptr(out))
+    return out
+
+
+def make_ycbcr_planes(rgb_like_seed: int, subsample: int, width: int, height: int, min_x: int = 0, min_y: int = 0):
+    """Random Y/Cb/Cr planes with the plane geometry image.NewYCbCr gives Rect(min_x, min_y, min_x+width, min_y+height)."""
+    xd = {0: 1, 1: 2, 2: 2, 3: 1, 4: 4, 5: 4}[subsample]
+    yd = {0: 1, 1: 1, 2: 2, 3: 2, 4: 1, 5: 2}[subsample]
+    cw = (min_x + width - 1) // xd - min_x // xd + 1
+    ch = (min_y + height - 1) // yd - min_y // yd + 1
+    rng = np.random.default_rng(rgb_like_seed)
+    y = rng.integers(0, 256, size=(height, width + 3), dtype=np.uint8)        # YStride > width on purpose
+    cb = rng.integers(0, 256, size=(ch, cw + 2), dtype=np.uint8)
+    cr = rng.integers(0, 256, size=(ch, cw + 2), dtype=np.uint8)
+    return y, cb, cr

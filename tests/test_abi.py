@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/pigo_b200.h but not exported"
     assert sorted(declared) == sorted(pigo_b200.ABI_SYMBOLS)
-    assert L.pigo_version() == 100
+    assert L.pigo_version() == 200
 
 
 def test_host_side_ladder_matches_oracle():

@@ -64,3 +64,42 @@ def test_gather_restores_single_gpu_order_world2():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert ok == (True, True)
+
+
+def _worker_pipeline(rank, world, port, nframes, cap, ncalls, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = pd.shard_range(nframes, rank, world)
+    per = -(-nframes // world)
+    rng = np.random.default_rng(7)
+    all_n = rng.integers(0, cap + 1, size=nframes).astype(np.int32)
+    all_f = rng.integers(0, 2000, size=(nframes, cap, 4)).astype(np.int32)
+    all_p = rng.integers(-5, 2000, size=(nframes, cap, 2 + ncalls, 4)).astype(np.int32)
+    f = torch.zeros((per, cap, 4), dtype=torch.int32)
+    n = torch.zeros(per, dtype=torch.int32)
+    p = torch.zeros((per, cap, 2 + ncalls, 4), dtype=torch.int32)
+    f[:hi - lo] = torch.from_numpy(all_f[lo:hi]); n[:hi - lo] = torch.from_numpy(all_n[lo:hi]); p[:hi - lo] = torch.from_numpy(all_p[lo:hi])
+    res = pd.gather_pipeline(f, n, p, dst=0)
+    if rank == 0:
+        mf, mn, mp_ = pd.merge_pipeline(*res, nframes)
+        q.put((np.array_equal(mf.numpy(), all_f), np.array_equal(mn.numpy(), all_n), np.array_equal(mp_.numpy(), all_p)))
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pipeline_gather_restores_frame_order_world2():
+    """The landmark gather of BASELINE configs[4] (faces + 2 eyes + 15 landmark points per face slot), world size 2 over gloo."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_pipeline, args=(r, 2, port, 5, 3, 15, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok == (True, True, True)

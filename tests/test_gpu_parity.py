@@ -449,3 +449,239 @@ def test_rotated_very_wide_frame_uses_64bit_coordinates(gpu_face, oracle_face):
         assert_same(g, oracle_face.run_cascade(img, 48, 33000, 33000, 20, 40, 0.2, 1.2, a))
     g = gpu_face.run_cascade_array(cp_of(img, 48, 33000, 33000, (20, 40, 0.2, 1.2)), 0.0)
     assert_same(g, oracle_face.run_cascade(img, 48, 33000, 33000, 20, 40, 0.2, 1.2, 0.0))
+
+
+# ================================================================================================================
+# round 2
+# ================================================================================================================
+@pytest.fixture(scope="module")
+def frame_4k():
+    return synth.frame_faces(None, 2160, 3840, shift=(5, 9), noise_seed=4)
+
+
+@pytest.mark.parametrize("k", list(range(1, 33)))
+def test_4k_rotated_every_table_slot(gpu_face, oracle_face, frame_4k, k):
+    """BASELINE configs[3]: 3840x2160, a = k/32 for EVERY table slot (core/pigo.go:156-160); the table-driven block/deep
+    kernels against the oracle, integer-exact and in emission order."""
+    g = gpu_face.run_cascade_array(cp_of(frame_4k, 2160, 3840, 3840, TEST_PARAMS), k / 32.0)
+    assert_same(g, oracle_face.run_cascade(frame_4k, 2160, 3840, 3840, *TEST_PARAMS, k / 32.0))
+
+
+@pytest.fixture
+def restore_round2_options():
+    keys = ["rot_mode", "puploc_mode", "deep_group", "gather_ks", "gather_ni", "host_first", "sub_batch", "gather_block"]
+    saved = {k: pigo_b200.get_option(k) for k in keys}
+    yield
+    for k, v in saved.items():
+        pigo_b200.set_option(k, v)
+
+
+@pytest.mark.parametrize("variant", [{"rot_mode": 1}, {"rot_mode": 0, "gather_ks": 4, "deep_group": 8}, {"rot_mode": 0, "gather_ni": 2, "deep_group": 16},
+                                     {"rot_mode": 0, "gather_ks": 468, "deep_group": 32}, {"rot_mode": 0, "gather_block": 8, "sub_batch": 1}])
+def test_rotated_kernel_variants(gpu_face, oracle_face, sample_gray, restore_round2_options, variant):
+    """Universal gather kernel vs table-driven kernels, tiny / whole resident prefix (everything / nothing through the deep kernel)."""
+    for k, v in variant.items():
+        pigo_b200.set_option(k, v)
+    wide = synth.frame_faces(sample_gray, 300, 900, noise_seed=1)       # cols > rows: the nrows-1 column clamp bites
+    tall = synth.frame_faces(sample_gray, 700, 260, noise_seed=2)
+    for img, r, c in ((sample_gray, 400, 320), (wide, 300, 900), (tall, 700, 260)):
+        for a in (1 / 32.0, 0.26, 0.5, 0.77, 1.0):
+            g = gpu_face.run_cascade_array(cp_of(img, r, c, c, TEST_PARAMS), a)
+            assert_same(g, oracle_face.run_cascade(img, r, c, c, *TEST_PARAMS, a))
+    frames = synth.make_batch(3, 360, 640, "FSU", seed0=41)
+    dets, cnt = gpu_face.RunCascadeBatch(frames, cp_of(None, 360, 640, 640, DOC_PARAMS), 0.4, cap_per_frame=64)
+    for f in range(3):
+        o = oracle_face.run_cascade(frames[f], 360, 640, 640, *DOC_PARAMS, 0.4)
+        assert cnt[f] == len(o) and dets[f, :cnt[f]].tobytes() == o.tobytes()
+
+
+def test_min_size_zero_is_a_valid_ladder(gpu_face, oracle_face):
+    """MinSize 0: scale 0 gives step 1, offset 1 and every node compares a pixel with itself (core/pigo.go:226-231); the
+    reference handles it, so does the library.  Negative sizes are rejected (the reference indexes out of bounds)."""
+    img = np.random.default_rng(3).integers(0, 256, size=(40, 50), dtype=np.uint8)
+    for prm in ((0, 30, 0.1, 1.3), (0, 0, 0.2, 1.1), (1, 9, 0.5, 1.5)):
+        g = gpu_face.run_cascade_array(cp_of(img, 40, 50, 50, prm), 0.0, cap=16)
+        assert_same(g, oracle_face.run_cascade(img, 40, 50, 50, *prm, 0.0))
+        assert pigo_b200.count_windows(40, 50, *prm) == O.count_windows(40, 50, *prm)
+    with pytest.raises(pigo_b200.PigoError):
+        gpu_face.run_cascade_array(cp_of(img, 40, 50, 50, (-4, 30, 0.1, 1.3)), 0.0)
+
+
+def test_host_frames_with_tight_stride_and_short_last_frame(gpu_face, oracle_face):
+    """Dim > Cols with the frames packed (rows-1)*Dim + Cols bytes apart -- the smallest buffer the reference can index
+    (the host path must not read rows*dim bytes per frame, and the 2-D copy must accept the tight pitch)."""
+    rows, cols, dim, nf = 120, 150, 160, 5
+    tight = (rows - 1) * dim + cols
+    buf = np.zeros(nf * tight, dtype=np.uint8)
+    imgs = []
+    for f in range(nf):
+        full = np.zeros((rows, dim), dtype=np.uint8)
+        full[:, :cols] = synth.frame_faces(None, rows, cols, shift=(7 * f, 3 * f), noise_seed=60 + f)
+        flat = full.reshape(-1)[:tight]
+        buf[f * tight:(f + 1) * tight] = flat
+        imgs.append(flat.copy())
+    import ctypes as C
+    cap = 256
+    out = np.zeros((nf, cap), dtype=pigo_b200.DET_DTYPE)
+    cnt = np.zeros(nf, dtype=np.int32)
+    prm = (20, 100, 0.1, 1.1)
+    rc = pigo_b200.lib().pigo_run_cascade_batch(gpu_face._h, buf.ctypes.data, nf, tight, rows, cols, dim, prm[0], prm[1], prm[2], prm[3], 0.0,
+                                                out.ctypes.data, cap, cnt.ctypes.data, 0, None)
+    assert rc == 0, pigo_b200.lib().pigo_last_error()
+    for f in range(nf):
+        padded = np.zeros(rows * dim, dtype=np.uint8)
+        padded[:tight] = imgs[f]
+        o = oracle_face.run_cascade(padded, rows, cols, dim, *prm, 0.0)
+        assert cnt[f] == len(o) and out[f, :cnt[f]].tobytes() == o.tobytes()
+
+
+@pytest.mark.parametrize("host_first", [0, 2, 16])
+def test_host_group_ramp_matches_uniform_groups(gpu_face, oracle_face, restore_round2_options, host_first):
+    """Host frames are scanned in groups that ramp up (16, 48, 64, 128 by default) so that only a short first copy is
+    exposed; the result must not depend on the grouping."""
+    pigo_b200.set_option("host_first", host_first)
+    frames = synth.make_batch(11, 270, 480, "USF", seed0=77)
+    dets, cnt = gpu_face.RunCascadeBatch(frames, cp_of(None, 270, 480, 480, TEST_PARAMS), 0.0, cap_per_frame=128)
+    for f in range(11):
+        o = oracle_face.run_cascade(frames[f], 270, 480, 480, *TEST_PARAMS, 0.0)
+        assert cnt[f] == len(o) and dets[f, :cnt[f]].tobytes() == o.tobytes()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_puploc_kernels_agree_with_oracle(sample_gray, restore_round2_options, mode):
+    """Both RunDetector kernels ((perturbation, tree)-pair kernel and warp-per-perturbation kernel), rotated and not,
+    flips, Perturbs 0..63, seeds near and beyond the image border, on a frame batch."""
+    pigo_b200.set_option("puploc_mode", mode)
+    rng = np.random.default_rng(123)
+    frames = np.stack([sample_gray, np.roll(sample_gray, 13, axis=1), 255 - sample_gray])
+    for pkname in ("puploc", "lps/lp93"):
+        pk = pigo_b200.load_cascade(pkname)
+        plc = pigo_b200.NewPuplocCascade().UnpackCascade(pk)
+        ora = O.OraclePuploc(pk)
+        for ang in (0.0, 0.2, 0.93):
+            seeds, flips, rnds, sfr = [], [], [], []
+            for k in range(30):
+                seeds.append(Puploc(int(rng.integers(-20, 420)), int(rng.integers(-20, 340)), float(np.float32(rng.uniform(2, 300))),
+                                    int(rng.integers(0, 64))))
+                flips.append(bool(rng.integers(0, 2)))
+                rnds.append(rng.random(189, dtype=np.float32))
+                sfr.append(int(rng.integers(0, 3)))
+            out = plc.run_detector_frames(seeds, sfr, frames, 3, 400 * 320, 400, 320, 320, ang, flips, np.stack(rnds))
+            for s, f, r, fr, o in zip(seeds, flips, rnds, sfr, out):
+                e = ora.run_detector(s.Row, s.Col, s.Scale, s.Perturbs, r, frames[fr], 400, 320, 320, ang, f)
+                assert (o.Row, o.Col) == (e[0], e[1]) and np.float32(o.Scale) == e[2]
+
+
+def _pipeline_cascades():
+    from pigo_b200 import pipeline
+    plc = pigo_b200.NewPuplocCascade().UnpackCascade(pigo_b200.load_cascade("puploc"))
+    names = sorted(set(pipeline.EYE_CASCADES + pipeline.MOUTH_CASCADES))
+    flp = {n: pigo_b200.NewPuplocCascade().UnpackCascade(pigo_b200.load_cascade("lps/" + n)) for n in names}
+    oplc = O.OraclePuploc(pigo_b200.load_cascade("puploc"))
+    oflp = {n: O.OraclePuploc(pigo_b200.load_cascade("lps/" + n)) for n in names}
+    return plc, flp, oplc, oflp
+
+
+def _check_pipeline_against_oracle(got, frames, rows, cols, oracle_face, oplc, oflp, randoms, face_cap, eye_perturbs=50, angle=0.0):
+    from pigo_b200 import pipeline
+    calls = pipeline.landmark_calls()
+    nrefined = 0
+    for f in range(len(frames)):
+        d = oracle_face.run_cascade(frames[f], rows, cols, cols, *TEST_PARAMS, angle)
+        _, cl = O.cluster(d, 0.1)
+        assert len(cl) <= face_cap
+        assert [(int(x["row"]), int(x["col"]), int(x["scale"])) for x in cl] == [fc.det[:3] for fc in got[f]]
+        for k, (c, fc) in enumerate(zip(cl, got[f])):
+            assert np.float32(c["q"]) == np.float32(fc.det[3])
+            if c["scale"] <= 50:
+                assert fc.left_eye is None
+                continue
+            nrefined += 1
+            ls, rs = pipeline.eye_seeds(int(c["row"]), int(c["col"]), int(c["scale"]), eye_perturbs)
+            le = oplc.run_detector(ls.Row, ls.Col, ls.Scale, eye_perturbs, randoms[f, k, 0], frames[f], rows, cols, cols, angle)
+            re_ = oplc.run_detector(rs.Row, rs.Col, rs.Scale, eye_perturbs, randoms[f, k, 1], frames[f], rows, cols, cols, angle)
+            assert (fc.left_eye.Row, fc.left_eye.Col, np.float32(fc.left_eye.Scale)) == (le[0], le[1], le[2])
+            assert (fc.right_eye.Row, fc.right_eye.Col, np.float32(fc.right_eye.Scale)) == (re_[0], re_[1], re_[2])
+            r0, c0, s0 = O.landmark_seed(le[0], le[1], re_[0], re_[1])
+            for ci, ((name, flip), lm) in enumerate(zip(calls, fc.landmarks)):
+                e = oflp[name].run_detector(r0, c0, float(s0), 63, randoms[f, k, 2 + ci], frames[f], rows, cols, cols, 0.0, flip)
+                assert (lm.Row, lm.Col, np.float32(lm.Scale)) == (e[0], e[1], e[2])
+    return nrefined
+
+
+@pytest.mark.parametrize("angle", [0.0, 0.03])
+def test_device_pipeline_vs_oracle(gpu_face, oracle_face, sample_gray, angle):
+    """pigo_detect_batch: the whole face -> cluster -> eye seeds -> RunDetector x2 -> landmark seeds ->
+    15 x RunDetector sequence on the device in one call, replayed step by step on the CPU oracle with the same injected
+    randoms (core/flploc_test.go:75-154; angle > 0 like cmd/pigo/main.go:422 passes det.angle to the eye RunDetector)."""
+    from pigo_b200 import pipeline
+    plc, flp, oplc, oflp = _pipeline_cascades()
+    frames = np.stack([synth.frame_faces(sample_gray, 540, 960, shift=(40 * i, 25 * i), noise_seed=30 + i) for i in range(3)] +
+                      [synth.frame_noise(540, 960, 5)])
+    cp = cp_of(None, 540, 960, 960, TEST_PARAMS)
+    face_cap = 24
+    randoms = np.random.default_rng(8).random((4, face_cap, 17, 63, 3), dtype=np.float32)
+    got = pipeline.detect_batch_device(gpu_face, plc, flp, frames, cp, iou=0.1, face_cap=face_cap, randoms=randoms, angle=angle)
+    n = _check_pipeline_against_oracle(got, frames, 540, 960, oracle_face, oplc, oflp, randoms, face_cap, angle=angle)
+    assert n >= 3 or angle > 0
+    assert got[3] == [] or all(fc.left_eye is None or fc.det[2] > 50 for fc in got[3])
+    # resident frames give the same answer
+    df = pigo_b200.DeviceFrames(frames)
+    try:
+        got2 = pipeline.detect_batch_device(gpu_face, plc, flp, df, cp, iou=0.1, face_cap=face_cap, randoms=randoms, angle=angle)
+    finally:
+        df.free()
+    assert got2 == got
+
+
+def test_device_pipeline_capacity_and_rng_mode(gpu_face, sample_gray):
+    """face_cap / det_cap too small -> PIGO_E_CAP (with the required count); library generator: deterministic, and
+    independent of how the batch is split (keys are (seed, frame, cluster, call))."""
+    from pigo_b200 import pipeline
+    plc, flp, _, _ = _pipeline_cascades()
+    frames = np.stack([synth.frame_faces(sample_gray, 540, 960, shift=(11 * i, 7 * i), noise_seed=90 + i) for i in range(4)])
+    cp = cp_of(None, 540, 960, 960, TEST_PARAMS)
+    with pytest.raises(pigo_b200.PigoError) as e:
+        pipeline.detect_batch_device(gpu_face, plc, flp, frames, cp, face_cap=1)
+    assert e.value.status == pigo_b200.PIGO_E_CAP
+    with pytest.raises(pigo_b200.PigoError) as e:
+        pipeline.detect_batch_device(gpu_face, plc, flp, frames, cp, face_cap=16, det_cap=2)
+    assert e.value.status == pigo_b200.PIGO_E_CAP
+    a = pipeline.detect_batch_device(gpu_face, plc, flp, frames, cp, face_cap=16, rng_seed=5, raw=True)
+    b = pipeline.detect_batch_device(gpu_face, plc, flp, frames, cp, face_cap=16, rng_seed=5, raw=True)
+    c = pipeline.detect_batch_device(gpu_face, plc, flp, frames, cp, face_cap=16, rng_seed=6, raw=True)
+    assert all(x.tobytes() == y.tobytes() for x, y in zip(a, b))
+    assert a[0].tobytes() == c[0].tobytes() and a[2].tobytes() != c[2].tobytes()
+    assert (a[2]["row"][a[0]["scale"] > 50] > 0).all()
+    # sharded entry point (one device selected: same code path as N devices, shard 0 only)
+    pigo_b200.init_devices(1)
+    s = pipeline.detect_batch_device(gpu_face, plc, flp, frames, cp, face_cap=16, rng_seed=5, raw=True, sharded=True)
+    assert all(x.tobytes() == y.tobytes() for x, y in zip(a, s))
+
+
+def test_sharded_scan_matches_single_device(gpu_face, oracle_face):
+    """pigo_run_cascade_batch_sharded over every visible device (1 on the default test box, 2+ under gpurun --gpus N):
+    frame shards, replicas built on first use, results in frame order == the per-frame oracle."""
+    n = pigo_b200.device_count()
+    pigo_b200.init_devices((1 << n) - 1)
+    try:
+        frames = synth.make_batch(7, 360, 640, "FUS", seed0=14)
+        dets, cnt = gpu_face.RunCascadeBatchSharded(frames, cp_of(None, 360, 640, 640, TEST_PARAMS), 0.0, cap_per_frame=2)   # forces the retry
+        for f in range(7):
+            o = oracle_face.run_cascade(frames[f], 360, 640, 640, *TEST_PARAMS, 0.0)
+            assert cnt[f] == len(o) and dets[f, :cnt[f]].tobytes() == o.tobytes()
+    finally:
+        pigo_b200.init(0)
+
+
+@pytest.mark.parametrize("subsample", [0, 1, 2, 3, 4, 5])
+def test_ycbcr_to_nrgba_matches_oracle(subsample):
+    """ImgToNRGBA for *image.YCbCr (core/image.go:60-76, section 8f N3): bit-exact against the restated Go conversion for the six
+    subsample ratios of core/image_test.go:21-57, non-zero rectangle origin, strides wider than the planes; fused gray =
+    RgbToGrayscale of the converted image."""
+    for (w, h, mx, my) in ((16, 16, 0, 0), (37, 21, 0, 0), (33, 18, 3, 5), (1920, 1080, 0, 0)):
+        y, cb, cr = O.make_ycbcr_planes(100 * subsample + w, subsample, w, h, mx, my)
+        got, gray = pigo_b200.YCbCrToNRGBA(y, cb, cr, subsample, w, h, mx, my, want_gray=True)
+        exp = O.ycbcr_to_nrgba(y, cb, cr, subsample, w, h, mx, my)
+        assert np.array_equal(got, exp)
+        assert np.array_equal(gray, O.rgba_to_gray(exp))

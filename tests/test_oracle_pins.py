@@ -173,3 +173,26 @@ def test_c_and_numpy_agree_on_random_cascades_of_any_depth(depth, ntrees):
         assert [(x["row"], x["col"], x["scale"], x["q"]) for x in a] == [(y[0], y[1], y[2], y[3]) for y in b]
         total += len(a)
     assert total > 0
+
+
+def test_ycbcr_restatement_is_within_one_of_the_reference_tests_formula():
+    """core/image_test.go:92-148 restates the YCbCr->RGB conversion with ROUNDING ((yy<<16 + 91881*cr + 1<<15) >> 16) and accepts
+    a difference of 1 against ImgToNRGBA (color.YCbCrToRGB, which truncates after multiplying y by 0x10101): the oracle's
+    restatement of the latter must satisfy the same pin for the six subsample ratios the test covers."""
+    import oracle_lib as O
+    for sub in range(6):
+        for (w, h, mx, my) in ((16, 16, 0, 0), (31, 17, 2, 3)):
+            y, cb, cr = O.make_ycbcr_planes(7 * sub + w, sub, w, h, mx, my)
+            got = O.ycbcr_to_nrgba(y, cb, cr, sub, w, h, mx, my).astype(np.int64)
+            xd = {0: 1, 1: 2, 2: 2, 3: 1, 4: 4, 5: 4}[sub]
+            yd = {0: 1, 1: 1, 2: 2, 3: 2, 4: 1, 5: 2}[sub]
+            for dy in range(h):
+                for dx in range(w):
+                    yy = int(y[dy, dx])
+                    ci, cj = (my + dy) // yd - my // yd, (mx + dx) // xd - mx // xd
+                    b_, r_ = int(cb[ci, cj]) - 128, int(cr[ci, cj]) - 128
+                    r = min(255, max(0, (yy * 65536 + 91881 * r_ + 32768) >> 16))
+                    g = min(255, max(0, (yy * 65536 - 22554 * b_ - 46802 * r_ + 32768) >> 16))
+                    b = min(255, max(0, (yy * 65536 + 116130 * b_ + 32768) >> 16))
+                    assert abs(got[dy, dx, 0] - r) <= 1 and abs(got[dy, dx, 1] - g) <= 1 and abs(got[dy, dx, 2] - b) <= 1
+                    assert got[dy, dx, 3] == 255
