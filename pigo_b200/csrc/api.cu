@@ -236,25 +236,13 @@ static int build_plan(int rows, int cols, int min_size, int max_size, double shi
 
 using namespace pigo;
 
-// Frames per pipeline group of one batch call.  Resident frames: uniform groups of 128 (fewest kernel tails).  Host frames:
-// the H2D copy of group k overlaps the scan of group k-1, so only the FIRST copy is exposed -- the groups ramp up
-// f, 3f, 4f, 8f, 8f, ... (f = host_first) and the scans follow right behind the copies (PCIe and the scan run at about the
-// same rate, ~26 frames/ms for 1080p).
-static std::vector<int> group_schedule(int nframes, bool frames_dev) {
+// Frames per pipeline group of one batch call: uniform groups, 128 frames by default (fewest kernel tails; the deferred
+// queues of a group stay bounded).  Host frames without in-kernel waiting (host_stream = 0): 64, because a whole group's
+// copy must finish before its scan starts and the first copy is exposed.
+static std::vector<int> group_schedule(int nframes, bool streamed) {
   std::vector<int> g;
   long long sub = g_opt.sub_batch.load();
-  const long long first = g_opt.host_first.load();
-  if (sub <= 0 && !frames_dev && first > 0) {
-    static const int mult[4] = {1, 3, 4, 8};
-    int left = nframes;
-    for (int k = 0; left > 0; ++k) {
-      const int n = (int)std::min<long long>(std::min<long long>(first * mult[std::min(k, 3)], 128), left);
-      g.push_back(n);
-      left -= n;
-    }
-    return g;
-  }
-  if (sub <= 0) sub = frames_dev ? 128 : 64;
+  if (sub <= 0) sub = streamed ? 128 : 64;
   for (int left = nframes; left > 0; left -= (int)sub) g.push_back((int)std::min<long long>(sub, left));
   return g;
 }
@@ -316,24 +304,35 @@ static int scan_batch_on(pigo_cascade* c, int dev, const uint8_t* frames, int nf
   // Sub-batch pipeline: the batch is cut into groups of frames (group_schedule) that alternate between `lanes` internal
   // streams.  (1) The deferred queues (Q1/Q2) of a group are bounded and consumed soon after they are filled;
   // (2) with host frames, the H2D copy of group k+1 overlaps the scan of group k.
-  const std::vector<int> groups = group_schedule(nframes, frames_dev);
-  const int nsub = (int)groups.size();
   int rot_slot = -1;
   if (angle > 0.0) {                      // core/pigo.go:232-236
     const double a = angle > 1.0 ? 1.0 : angle;
     rot_slot = (int)(32.0 * a);           // :159
   }
+  // Host frames, streamed: the copy stream moves the frames up chunk by chunk and bumps a ready counter after each chunk;
+  // the fused kernel (whose tile / block order is frame-major) waits in-kernel for the frame it is about to touch, so the
+  // scan runs right behind the copy at frame granularity instead of group granularity.  Only the fused kernel polls: the
+  // kernels queued behind it start after every frame of the group has arrived (stream wait on the group's last chunk).
+  const bool fused_path = rot_slot < 0 && c->depth == 6 && g_opt.scan_mode.load() == 0 && g_opt.tile_warps.load() > 0;
+  const bool streamed = !frames_dev && g_opt.host_stream.load() != 0 && fused_path;
+  const std::vector<int> groups = group_schedule(nframes, frames_dev || streamed);
+  const int nsub = (int)groups.size();
   int lanes = (int)std::min<long long>(std::max<long long>(1, g_opt.lanes.load()), kMaxLanes);
   if (nsub == 1 || rot_slot >= 0) lanes = 1;   // (the rotated node table is built once, on the first group's stream)
   if ((rc = w->ensure_lanes(lanes))) return rc;
 
   // counters: [0..nframes) raw counts | 8 x u64 work counters per sub-batch
   const size_t work_off = ((size_t)nframes * 4 + 15) & ~(size_t)15;
-  const size_t cnt_bytes = work_off + (size_t)nsub * 64 + 64;
+  const size_t cnt_bytes = work_off + (size_t)nsub * 64 + 128;
   if ((rc = w->counters.reserve(cnt_bytes))) return rc;
   CUDA_TRY(cudaMemsetAsync(w->counters.p, 0, cnt_bytes, st));
   int32_t* d_rawcount = (int32_t*)w->counters.p;
   unsigned long long* d_work = (unsigned long long*)((char*)w->counters.p + work_off);
+  unsigned int* d_ready = (unsigned int*)((char*)w->counters.p + work_off + (size_t)nsub * 64 + 64);
+  if (streamed && !w->seq) {
+    CUDA_TRY(cudaHostAlloc((void**)&w->seq, 65536 * sizeof(unsigned int), cudaHostAllocDefault));
+    for (unsigned i = 0; i < 65536; ++i) w->seq[i] = i + 1;
+  }
 
   if (lanes > 1 || !frames_dev) {
     CUDA_TRY(cudaEventRecord(w->ev_fork, st));   // everything queued on `st` so far (previous results, memset) comes first
@@ -349,21 +348,27 @@ static int scan_batch_on(pigo_cascade* c, int dev, const uint8_t* frames, int nf
     const int nf = groups[k];
     const int lane = k % lanes;
     cudaStream_t ls = lanes > 1 ? w->lane_stream[lane] : st;
+    cudaEvent_t ev_group = nullptr;
     if (!frames_dev) {
-      // the copy of group k runs on the copy stream and overlaps the scan of group k-1 (pinned source memory)
-      uint8_t* dst = (uint8_t*)w->frames.p + (size_t)f0 * d_stride;
-      const uint8_t* src = frames + (size_t)f0 * frame_stride;
+      // the copies run on the copy stream (pinned source memory) and overlap the scan
       cudaStream_t cs = w->copy_stream;
-      const bool last_group = f0 + nf == nframes;   // only the batch's last frame may be short; the others have a successor behind them
-      if (frame_stride == d_stride || nf == 1) {
-        CUDA_TRY(cudaMemcpyAsync(dst, src, d_stride * (size_t)(nf - 1) + (last_group ? frame_min : frame_bytes), cudaMemcpyHostToDevice, cs));
-      } else {
-        CUDA_TRY(cudaMemcpy2DAsync(dst, d_stride, src, frame_stride, frame_min, nf, cudaMemcpyHostToDevice, cs));
+      const long long chunk = streamed ? std::max<long long>(1, g_opt.copy_chunk.load()) : nf;
+      for (int c0 = 0; c0 < nf; c0 += (int)chunk) {
+        const int cn = (int)std::min<long long>(chunk, nf - c0);
+        uint8_t* dst = (uint8_t*)w->frames.p + (size_t)(f0 + c0) * d_stride;
+        const uint8_t* src = frames + (size_t)(f0 + c0) * frame_stride;
+        const bool last = f0 + c0 + cn == nframes;   // only the batch's last frame may be short; the others have a successor behind them
+        if (frame_stride == d_stride || cn == 1) {
+          CUDA_TRY(cudaMemcpyAsync(dst, src, d_stride * (size_t)(cn - 1) + (last ? frame_min : frame_bytes), cudaMemcpyHostToDevice, cs));
+        } else {
+          CUDA_TRY(cudaMemcpy2DAsync(dst, d_stride, src, frame_stride, frame_min, cn, cudaMemcpyHostToDevice, cs));
+        }
+        if (streamed) CUDA_TRY(cudaMemcpyAsync(d_ready, w->seq + (f0 + c0 + cn - 1), sizeof(unsigned int), cudaMemcpyHostToDevice, cs));
       }
-      cudaEvent_t ev = w->copy_event(k);
-      if (!ev) return set_err(PIGO_E_CUDA, "event creation failed");
-      CUDA_TRY(cudaEventRecord(ev, cs));
-      CUDA_TRY(cudaStreamWaitEvent(ls, ev, 0));
+      ev_group = w->copy_event(k);
+      if (!ev_group) return set_err(PIGO_E_CUDA, "event creation failed");
+      CUDA_TRY(cudaEventRecord(ev_group, cs));
+      if (!streamed) CUDA_TRY(cudaStreamWaitEvent(ls, ev_group, 0));
     }
     if (nscales > 0 && c->ntrees > 0) {
       ScanArgs A{};
@@ -372,9 +377,12 @@ static int scan_batch_on(pigo_cascade* c, int dev, const uint8_t* frames, int nf
       A.plan = (const ScaleEntry*)w->plan.p; A.nscales = nscales; A.wins_per_frame = (uint32_t)w->wins;
       A.rot_slot = rot_slot; A.rot_tab = nullptr; A.batch_frames = nframes;
       A.raw = (RawDet*)w->raw.p + (size_t)f0 * cap; A.raw_count = d_rawcount + f0; A.cap = cap;
+      A.frame_base = (uint32_t)f0; A.ready = streamed ? d_ready : nullptr;
+      w->group_copied = streamed ? ev_group : nullptr;
       rc = run_scan(R, w, lane, A, d_work + 8 * (size_t)k, ls, R->num_sms);
       if (rc) return rc;
     }
+    if (streamed && !(nscales > 0 && c->ntrees > 0)) CUDA_TRY(cudaStreamWaitEvent(ls, ev_group, 0));   // nothing polled: still order the stream behind the copy
     f0 += nf;
   }
   if (lanes > 1) {

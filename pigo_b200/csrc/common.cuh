@@ -40,10 +40,11 @@ struct RawDet {
 // A window whose evaluation continues in the deep kernel from tree `tree` with partial score `acc`.
 struct DeepItem {
   uint32_t wid;
-  int32_t frame;
+  uint32_t frame_si;   // frame (low 16 bits: < 65536 frames per call) | ladder entry (high 16 bits), so that the consumer needs no search
   int32_t tree;
   float acc;
 };
+__host__ __device__ __forceinline__ uint32_t pack_frame_si(int frame, int si) { return (uint32_t)frame | ((uint32_t)si << 16); }
 
 // Rotated scan (core/pigo.go:150-191).  65536*r + qcos*c0 - qsin*c1 is clamped at 0 and THEN shifted (:167), and
 //   max(0, 65536*r + x) >> 16  ==  max(0, r + (x >> 16))     for every integer r, x  (65536*r is a multiple of 65536),
@@ -87,8 +88,25 @@ struct ScanArgs {
   DeepItem* longq;
   unsigned int* long_count;
   uint32_t long_cap;
-  uint32_t pad2;
+  uint32_t frame_base;        // index of this group's first frame in the API call (for `ready`)
+  // Host frames streamed in while the scan runs: *ready = number of leading frames of the call whose H2D copy has completed
+  // (written by the copy stream after every chunk); a warp waits for its frame before it touches it.  nullptr = resident.
+  const unsigned int* ready;
 };
+
+// Waits until frame `need - 1` of the call has arrived (lane 0 polls with acquire semantics, the warp follows).
+__device__ __forceinline__ void wait_frames(const unsigned int* ready, unsigned need) {
+  if (ready == nullptr) return;
+  if ((threadIdx.x & 31) == 0) {
+    unsigned have;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(ready) : "memory");
+      if (have >= need) break;
+      __nanosleep(256);
+    }
+  }
+  __syncwarp();
+}
 
 // ---- tiled kernel -------------------------------------------------------------------------------------------
 constexpr int kTiledMaxThreads = 1024;

@@ -15,7 +15,57 @@
 
 namespace pigo {
 
-template <int GROUP, int ROT>
+// One tree (index t) of the window: the leaf value.  Unrotated: pc = the window's centre pixel; rotated: pc = the frame,
+// (r, c) the centre, rt = this scale's node table.
+template <int ROT>
+__device__ __forceinline__ float deep_walk(const ScanArgs& A, const FaceTables& T, const uint8_t* __restrict__ pc, const RotNode* __restrict__ rt,
+                                           int t, int r, int c, int s, int lim) {
+  const int2* tp2 = reinterpret_cast<const int2*>(T.preds + (size_t)t * 64);
+  int idx = 1;
+  if (ROT) {
+    // children of node idx are nodes 2idx, 2idx+1: adjacent 8-byte records, fetched with one 16-byte load while
+    // this node's two pixels are in flight
+    const RotNode* tn = rt + (size_t)t * 64;
+    uint2 cur = __ldg(reinterpret_cast<const uint2*>(tn + 1));
+    int leafbits = 0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      uint4 kids = make_uint4(0, 0, 0, 0);
+      int2 lv = make_int2(0, 0);
+      if (j < 5) kids = __ldg(reinterpret_cast<const uint4*>(tn + 2 * idx));
+      else lv = __ldg(tp2 + (idx - 32));
+      const int r1 = __vimin_s32_relu(r + (int)(short)(cur.x & 0xffff), lim), c1 = __vimin_s32_relu(c + ((int)cur.x >> 16), lim);
+      const int r2 = __vimin_s32_relu(r + (int)(short)(cur.y & 0xffff), lim), c2 = __vimin_s32_relu(c + ((int)cur.y >> 16), lim);
+      const unsigned p1 = __ldg(pc + (size_t)r1 * A.dim + c1), p2 = __ldg(pc + (size_t)r2 * A.dim + c2);
+      const bool right = p1 <= p2;                  // core/pigo.go:179
+      cur = right ? make_uint2(kids.z, kids.w) : make_uint2(kids.x, kids.y);
+      leafbits = right ? lv.y : lv.x;
+      idx = 2 * idx + (right ? 1 : 0);
+    }
+    return __int_as_float(leafbits);
+  } else {
+    // child-pair prefetch: both children of node idx (codes: bytes 8*idx.., leaves: floats 2*idx-64..) are fetched
+    // with one 64-bit load that is in flight together with the two pixel gathers
+    const int2* tc2 = reinterpret_cast<const int2*>(T.codes + (size_t)t * 256);
+    int cw = __ldg(reinterpret_cast<const int*>(tc2) + 1);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int2 kids = j < 5 ? __ldg(tc2 + idx) : __ldg(tp2 + (idx - 32));
+      const int o1 = (((int)(int8_t)(cw) * s) >> 8) * A.dim + (((int)(int8_t)(cw >> 8) * s) >> 8);
+      const int o2 = (((int)(int8_t)(cw >> 16) * s) >> 8) * A.dim + (((cw >> 24) * s) >> 8);
+      const unsigned p1 = __ldg(pc + o1), p2 = __ldg(pc + o2);
+      const bool right = p1 <= p2;                  // core/pigo.go:129-135
+      cw = right ? kids.y : kids.x;
+      idx = 2 * idx + (right ? 1 : 0);
+    }
+    return __int_as_float(cw);
+  }
+}
+
+// FLAT = 1: every iteration each lane group either fetches its next window or walks one step (no group waits for another
+// at a reconvergence point, but a fetch of one group delays the step of the others).  FLAT = 0: round-1 structure, the
+// groups of a warp fetch together and the warp stays in the step loop until its slowest window is done.
+template <int GROUP, int ROT, int FLAT>
 __global__ void __launch_bounds__(256) deep_kernel(const ScanArgs A, unsigned long long* counter) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -42,75 +92,32 @@ __global__ void __launch_bounds__(256) deep_kernel(const ScanArgs A, unsigned lo
         more = false;
       } else {
         const DeepItem it = A.longq[g];
-        const int si = find_scale(A.plan, A.nscales, it.wid);
+        const int si = (int)(it.frame_si >> 16);       // ladder entry, packed by the producer (no search here)
         const ScaleEntry e = A.plan[si];
         const uint32_t local = it.wid - e.wbase;
         const uint32_t ri = local / (uint32_t)e.ncols, ci = local - ri * (uint32_t)e.ncols;
-        s = e.s; wid = it.wid; frame = it.frame; t0 = it.tree; acc = it.acc;
+        s = e.s; wid = it.wid; frame = (int)(it.frame_si & 0xffffu); t0 = it.tree; acc = it.acc;
         r = e.off + (int)ri * e.step; c = e.off + (int)ci * e.step;
-        pc = A.frames + (size_t)it.frame * A.frame_stride;
+        pc = A.frames + (size_t)frame * A.frame_stride;
         if (ROT) rt = A.rot_tab + (size_t)si * T.ntrees * 64;
         else pc += (size_t)r * A.dim + c;
         have = true;
       }
     }
-    if (!__any_sync(FULL, have)) break;
-    if (have) {
+    if (FLAT ? !__any_sync(FULL, have) : !have) break;   // FLAT = 0: a group without work leaves; the others carry on
+    bool looping = have;
+    while (looping) {
       const int t = min(t0 + sub, T.ntrees - 1);        // lanes past the last tree redo it harmlessly
       const float thr = __ldg(T.thresh + t);
-      const int2* tp2 = reinterpret_cast<const int2*>(T.preds + (size_t)t * 64);
-      int idx = 1;
-      float pred;
-      if (ROT) {
-        // children of node idx are nodes 2idx, 2idx+1: adjacent 8-byte records, fetched with one 16-byte load while
-        // this node's two pixels are in flight
-        const RotNode* tn = rt + (size_t)t * 64;
-        uint2 cur = __ldg(reinterpret_cast<const uint2*>(tn + 1));
-        int leafbits = 0;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          uint4 kids = make_uint4(0, 0, 0, 0);
-          int2 lv = make_int2(0, 0);
-          if (j < 5) kids = __ldg(reinterpret_cast<const uint4*>(tn + 2 * idx));
-          else lv = __ldg(tp2 + (idx - 32));
-          const int r1 = __vimin_s32_relu(r + (int)(short)(cur.x & 0xffff), lim), c1 = __vimin_s32_relu(c + ((int)cur.x >> 16), lim);
-          const int r2 = __vimin_s32_relu(r + (int)(short)(cur.y & 0xffff), lim), c2 = __vimin_s32_relu(c + ((int)cur.y >> 16), lim);
-          const unsigned p1 = __ldg(pc + (size_t)r1 * A.dim + c1), p2 = __ldg(pc + (size_t)r2 * A.dim + c2);
-          const bool right = p1 <= p2;                  // core/pigo.go:179
-          cur = right ? make_uint2(kids.z, kids.w) : make_uint2(kids.x, kids.y);
-          leafbits = right ? lv.y : lv.x;
-          idx = 2 * idx + (right ? 1 : 0);
-        }
-        pred = __int_as_float(leafbits);
-      } else {
-        // child-pair prefetch: both children of node idx (codes: bytes 8*idx.., leaves: floats 2*idx-64..) are fetched
-        // with one 64-bit load that is in flight together with the two pixel gathers
-        const int2* tc2 = reinterpret_cast<const int2*>(T.codes + (size_t)t * 256);
-        int cw = __ldg(reinterpret_cast<const int*>(tc2) + 1);
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          const int2 kids = j < 5 ? __ldg(tc2 + idx) : __ldg(tp2 + (idx - 32));
-          const int o1 = (((int)(int8_t)(cw) * s) >> 8) * A.dim + (((int)(int8_t)(cw >> 8) * s) >> 8);
-          const int o2 = (((int)(int8_t)(cw >> 16) * s) >> 8) * A.dim + (((cw >> 24) * s) >> 8);
-          const unsigned p1 = __ldg(pc + o1), p2 = __ldg(pc + o2);
-          const bool right = p1 <= p2;                  // core/pigo.go:129-135
-          cw = right ? kids.y : kids.x;
-          idx = 2 * idx + (right ? 1 : 0);
-        }
-        pred = __int_as_float(cw);
-      }
-      // the reference's sequential accumulation, core/pigo.go:137-141, branch-free over the group's GROUP trees
+      const float pred = deep_walk<ROT>(A, T, pc, rt, t, r, c, s, lim);
+      // the reference's sequential accumulation, core/pigo.go:137-141
       const int nvalid = min(GROUP, T.ntrees - t0);
       bool rejected = false;
       float thr_last = 0.f;
-#pragma unroll
-      for (int j = 0; j < GROUP; ++j) {
-        const float pj = __shfl_sync(gmask, pred, leader + j), tj = __shfl_sync(gmask, thr, leader + j);
-        if (j < nvalid && !rejected) {
-          acc += pj;
-          thr_last = tj;
-          rejected = acc <= tj;
-        }
+      for (int j = 0; j < nvalid; ++j) {
+        acc += __shfl_sync(gmask, pred, leader + j);
+        thr_last = __shfl_sync(gmask, thr, leader + j);
+        if (acc <= thr_last) { rejected = true; break; }
       }
       t0 += GROUP;
       if (rejected) {
@@ -125,21 +132,23 @@ __global__ void __launch_bounds__(256) deep_kernel(const ScanArgs A, unsigned lo
         }
         have = false;
       }
+      looping = FLAT ? false : have;                    // FLAT: one step per outer iteration
     }
   }
 }
 
+template <int ROT, int FLAT>
+static void launch_deep_g(const ScanArgs& A, unsigned long long* counter, int grid, int group, cudaStream_t st) {
+  if (group == 8) deep_kernel<8, ROT, FLAT><<<grid, 256, 0, st>>>(A, counter);
+  else if (group == 16) deep_kernel<16, ROT, FLAT><<<grid, 256, 0, st>>>(A, counter);
+  else deep_kernel<32, ROT, FLAT><<<grid, 256, 0, st>>>(A, counter);
+}
+
 void launch_deep(const ScanArgs& A, unsigned long long* counter, int grid, int group, cudaStream_t st) {
   const bool rot = A.rot_slot >= 0 && A.rot_tab != nullptr;
-  if (rot) {
-    if (group == 8) deep_kernel<8, 1><<<grid, 256, 0, st>>>(A, counter);
-    else if (group == 16) deep_kernel<16, 1><<<grid, 256, 0, st>>>(A, counter);
-    else deep_kernel<32, 1><<<grid, 256, 0, st>>>(A, counter);
-  } else {
-    if (group == 8) deep_kernel<8, 0><<<grid, 256, 0, st>>>(A, counter);
-    else if (group == 16) deep_kernel<16, 0><<<grid, 256, 0, st>>>(A, counter);
-    else deep_kernel<32, 0><<<grid, 256, 0, st>>>(A, counter);
-  }
+  const bool flat = g_opt.deep_flat.load() != 0;
+  if (rot) { if (flat) launch_deep_g<1, 1>(A, counter, grid, group, st); else launch_deep_g<1, 0>(A, counter, grid, group, st); }
+  else { if (flat) launch_deep_g<0, 1>(A, counter, grid, group, st); else launch_deep_g<0, 0>(A, counter, grid, group, st); }
 }
 
 // ---- rotated node table -------------------------------------------------------------------------------------

@@ -40,8 +40,10 @@ struct Options {
   std::atomic<long long> gather_block{0};   // gather block edge in windows: 16, 8, or 0 = auto (8 for <= 4 frames)
   std::atomic<long long> deep_group{0};     // lanes (trees per step) per window in the deep kernel: 8, 16, 32; 0 = auto (32 for <= 4 frames: latency, else 8)
   std::atomic<long long> sub_batch{0};      // frames per pipeline group (0 = auto: 128 for resident frames; host frames: see host_first)
-  std::atomic<long long> host_first{16};    // host frames, sub_batch=0: group sizes ramp f, 3f, 4f, 8f, 8f.. (f = host_first, groups <= 128) so that the
-                                            // first H2D copy that nothing can hide is short; 0 = uniform 64-frame groups
+  std::atomic<long long> host_stream{1};    // host frames: 1 = the scan kernels start at once and wait IN-KERNEL for each frame's copy (a ready counter the copy
+                                            // stream bumps after every chunk), so copy and scan overlap frame by frame; 0 = per-group copy events (round 1)
+  std::atomic<long long> copy_chunk{8};     // host_stream: frames per H2D copy chunk
+  std::atomic<long long> deep_flat{0};      // deep kernel loop: 0 = groups of a warp fetch together (round 1), 1 = flat (fetch or step per iteration)
   std::atomic<long long> rot_mode{0};       // rotated scan: 0 = table-driven block kernel + deep kernel, 1 = universal gather kernel
   std::atomic<long long> puploc_mode{0};    // RunDetector kernel: 0 = (perturbation, tree)-pair kernel, 1 = warp-per-perturbation kernel
   std::atomic<long long> lanes{1};          // internal streams the groups alternate between
@@ -58,8 +60,8 @@ struct Options {
         {"tile_min_core_steps", &Options::tile_min_core_steps}, {"tile_prefetch", &Options::tile_prefetch},
          {"gather_block", &Options::gather_block}, {"deep_group", &Options::deep_group},
         {"sub_batch", &Options::sub_batch}, {"lanes", &Options::lanes}, {"tile_tail_min", &Options::tile_tail_min},
-        {"tile_band_ratio", &Options::tile_band_ratio}, {"timing", &Options::timing}, {"host_first", &Options::host_first},
-        {"rot_mode", &Options::rot_mode}, {"puploc_mode", &Options::puploc_mode}};
+        {"tile_band_ratio", &Options::tile_band_ratio}, {"timing", &Options::timing}, {"host_stream", &Options::host_stream}, {"copy_chunk", &Options::copy_chunk},
+        {"deep_flat", &Options::deep_flat}, {"rot_mode", &Options::rot_mode}, {"puploc_mode", &Options::puploc_mode}};
     for (const Entry& e : table)
       if (k == e.name) return &(this->*e.field);
     return nullptr;
@@ -141,6 +143,8 @@ struct Workspace {
   cudaStream_t active_stream = nullptr;        // stream of the call that currently borrows this workspace (see WsGuard)
   bool active_stream_set = false;
   cudaStream_t copy_stream = nullptr;          // H2D copies of host frames, one event per pipeline group
+  cudaEvent_t group_copied = nullptr;          // streamed host frames: the current group's "all chunks copied" event (run_scan orders
+                                               // the kernels behind the polling fused kernel after it)
   std::vector<cudaEvent_t> copy_events;
   cudaEvent_t copy_event(int k) {
     while ((int)copy_events.size() <= k) {
@@ -168,6 +172,7 @@ struct Workspace {
   double p_shift = 0, p_scale = 0;
   void* pinned = nullptr;
   size_t pinned_cap = 0;
+  unsigned int* seq = nullptr;                 // pinned 1, 2, 3, ...: source of the ready-counter updates (host_stream)
   ~Workspace() {
     frames.release(); raw.release(); counters.release(); out.release(); nout.release(); plan.release();
     for (int l = 0; l < kMaxLanes; ++l) {
@@ -181,6 +186,7 @@ struct Workspace {
     if (copy_stream) cudaStreamDestroy(copy_stream);
     tiles.release(); scratch_a.release(); scratch_b.release(); scratch_c.release(); rot_tab.release();
     if (pinned) cudaFreeHost(pinned);
+    if (seq) cudaFreeHost(seq);
     if (stream) cudaStreamDestroy(stream);
   }
 };

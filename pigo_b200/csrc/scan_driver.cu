@@ -303,9 +303,16 @@ int run_scan(FaceReplica* c, Workspace* w, int lane, ScanArgs& A, unsigned long 
     }
   }
 
+  // Streamed host frames: only the fused kernel waits in-kernel for its frames.  Everything queued behind it is ordered after
+  // the group's last copy chunk (which the fused kernel has already seen, so this wait is free), and if the fused kernel
+  // did not run for this geometry the same wait is what orders the scan behind the copy.
+  if (A.ready != nullptr && w->group_copied != nullptr) {
+    if (cudaStreamWaitEvent(st, w->group_copied, 0) != cudaSuccess) return set_err(PIGO_E_CUDA, "cudaStreamWaitEvent failed");
+  }
   // ---- gather-v2: the Q1 stragglers of the tile warps + the 16x16-window blocks of the untiled scales
   {
     TiledArgs G = T;
+    G.scan.ready = nullptr;
     G.ks = round_ks(g_opt.gather_ks.load());
     G.consume_q1 = tiled_ran ? 1 : 0;
     G.tile_warps = 0;

@@ -112,11 +112,11 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
   // the (scale, tree) node table in S.rot_tab (units of 64 RotNode records; advances by one per tree).
   bool alive[NG];
   const uint8_t* pc[NG];
-  int sv[NG], fr[NG], wr[NG], wc[NG];
+  int sv[NG], fr[NG], wr[NG], wc[NG], wsi[NG];   // wsi = ladder entry of the window (travels with queue items)
   uint32_t tbo[NG], wid[NG];
   float acc[NG];
 #pragma unroll
-  for (int u = 0; u < NG; ++u) { alive[u] = false; pc[u] = S.frames; sv[u] = 0; fr[u] = 0; wr[u] = 0; wc[u] = 0; tbo[u] = casc; wid[u] = 0; acc[u] = 0.f; }
+  for (int u = 0; u < NG; ++u) { alive[u] = false; pc[u] = S.frames; sv[u] = 0; fr[u] = 0; wr[u] = 0; wc[u] = 0; wsi[u] = 0; tbo[u] = casc; wid[u] = 0; acc[u] = 0.f; }
   // per-warp block cursor (uniform)
   uint32_t cur = 0, end = 0;
   int b_s = 0, b_step = 0, b_r0 = 0, b_c0 = 0, b_w = 1, b_ncols = 0, cframe = 0, b_si = 0;
@@ -152,6 +152,7 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
             break;
           }
           cframe = (int)(g / A.gather_blocks_per_frame);
+          wait_frames(S.ready, S.frame_base + (unsigned)cframe + 1u);
           const uint32_t bidx = (uint32_t)(g % A.gather_blocks_per_frame);
           int lo = A.gather_scale_lo, hi = S.nscales - 1;   // ladder entry whose block range contains bidx
           while (lo < hi) {
@@ -178,21 +179,21 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
           const uint32_t k = cur + rank;
           if (from_q1) {
             const DeepItem it = S.deep[k];
-            const int si = find_scale(S.plan, S.nscales, it.wid);
+            const int si = (int)(it.frame_si >> 16), itf = (int)(it.frame_si & 0xffffu);
             const ScaleEntry e = S.plan[si];
             const uint32_t local = it.wid - e.wbase;
             const uint32_t ri = local / (uint32_t)e.ncols, ci = local - ri * (uint32_t)e.ncols;
-            wid[u] = it.wid; fr[u] = it.frame;
+            wid[u] = it.wid; fr[u] = itf; wsi[u] = si;
             const int r = e.off + (int)ri * e.step, c = e.off + (int)ci * e.step;
-            if (ROT) { pc[u] = S.frames + (size_t)it.frame * S.frame_stride; wr[u] = r; wc[u] = c; sv[u] = si * T.ntrees + it.tree; }
-            else { pc[u] = S.frames + (size_t)it.frame * S.frame_stride + (size_t)r * S.dim + c; sv[u] = e.s; }
+            if (ROT) { pc[u] = S.frames + (size_t)itf * S.frame_stride; wr[u] = r; wc[u] = c; sv[u] = si * T.ntrees + it.tree; }
+            else { pc[u] = S.frames + (size_t)itf * S.frame_stride + (size_t)r * S.dim + c; sv[u] = e.s; }
             tbo[u] = casc + (uint32_t)it.tree * kTreeRec; acc[u] = it.acc;
           } else {
             const uint32_t ly = b_w == (1 << A.gb_shift) ? (k >> A.gb_shift) : k / (uint32_t)b_w;
             const uint32_t lx = k - ly * (uint32_t)b_w;
             const int r = b_r0 + (int)ly * b_step, c = b_c0 + (int)lx * b_step;
             wid[u] = b_wid0 + ly * (uint32_t)b_ncols + lx;
-            fr[u] = cframe;
+            fr[u] = cframe; wsi[u] = b_si;
             if (ROT) { pc[u] = S.frames + (size_t)cframe * S.frame_stride; wr[u] = r; wc[u] = c; sv[u] = b_si * T.ntrees; }
             else { pc[u] = S.frames + (size_t)cframe * S.frame_stride + (size_t)r * S.dim + c; sv[u] = b_s; }
             tbo[u] = casc; acc[u] = 0.f;
@@ -294,7 +295,7 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
           // the window simply continues here on the global tables
           const unsigned pos = atomicAdd(S.long_count, 1u);
           if (pos < S.long_cap) {
-            S.longq[pos] = DeepItem{wid[u], fr[u], (int)((tbo[u] - casc) / kTreeRec), acc[u]};
+            S.longq[pos] = DeepItem{wid[u], pack_frame_si(fr[u], wsi[u]), (int)((tbo[u] - casc) / kTreeRec), acc[u]};
             alive[u] = false;
           }
         }
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
     tg = __shfl_sync(FULL, tg, 0);
     if (tg >= A.total_tiles) break;
     const int frame = (int)(tg / A.tiles_per_frame);
+    wait_frames(S.ready, S.frame_base + (unsigned)frame + 1u);
     int tf = (int)(tg % A.tiles_per_frame);
     int b = 0;
     while (b + 1 < A.nbands && tf >= A.band[b].ntiles) { tf -= A.band[b].ntiles; ++b; }
@@ -493,8 +495,11 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
               if (lane == 0) qbase = atomicAdd(S.deep_count, (unsigned)__popc(live));
               qbase = __shfl_sync(FULL, qbase, 0);
               const unsigned pos = qbase + __popc(live & lanemask_lt());
+              int qsi = B.scale_lo;                 // ladder entry of this lane's window: lane k of the warp describes band scale k
+              for (int k = 0; k < B.nscales; ++k)
+                if (__shfl_sync(FULL, e.s, k) == sv[u]) qsi = B.scale_lo + k;
               if (alive[u] && pos < S.deep_cap) {
-                S.deep[pos] = DeepItem{wid[u], frame, (int)((tbo[u] - casc) / kTreeRec), acc[u]};
+                S.deep[pos] = DeepItem{wid[u], pack_frame_si(frame, qsi), (int)((tbo[u] - casc) / kTreeRec), acc[u]};
                 alive[u] = false;
               }
               live = __ballot_sync(FULL, alive[u]);
@@ -599,9 +604,12 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
               qbase = __shfl_sync(FULL, qbase, 0);
               const unsigned pos = qbase + __popc(mb & lanemask_lt());
               bool failed = false;
+              int qsi = B.scale_lo;
+              for (int k = 0; k < B.nscales; ++k)
+                if (__shfl_sync(FULL, e.s, k) == sv[u]) qsi = B.scale_lo + k;
               if (at_end) {
                 if (pos < S.long_cap) {
-                  S.longq[pos] = DeepItem{wid[u], frame, A.ks, acc[u]};
+                  S.longq[pos] = DeepItem{wid[u], pack_frame_si(frame, qsi), A.ks, acc[u]};
                   alive[u] = false;
                 } else {
                   failed = true;

@@ -79,7 +79,7 @@ def test_empty_and_degenerate_inputs(gpu_face, oracle_face):
     g = gpu_face.run_cascade_array(cp_of(img, 120, 100, 100, (30, 60, 0.0, 1.5)), 0.0)
     assert_same(g, oracle_face.run_cascade(img, 120, 100, 100, 30, 60, 0.0, 1.5, 0.0))
     with pytest.raises(pigo_b200.PigoError):
-        gpu_face.run_cascade_array(cp_of(img, 120, 100, 100, (0, 60, 0.1, 1.5)), 0.0)          # MinSize 0: reference would panic
+        gpu_face.run_cascade_array(cp_of(img, 120, 100, 100, (-2, 60, 0.1, 1.5)), 0.0)         # negative MinSize: the reference would panic
 
 
 @pytest.mark.parametrize("cls", ["U", "S", "F"])
@@ -260,13 +260,15 @@ VARIANTS = [
     {"scan_mode": 3, "gather_block": 16, "gather_ni": 2},
     {"scan_mode": 3, "gather_ks": 4},                                                   # nearly everything through the deep kernel
     {"scan_mode": 0, "gather_ks": 468, "tile_ks": 468, "tile_warps": 4, "gather_warps": 0},   # whole cascade resident: no Q2
+    {"scan_mode": 0, "deep_flat": 1, "deep_group": 8, "tile_ks": 6},                          # flat deep loop, lots of Q2 traffic
+    {"scan_mode": 3, "deep_flat": 1, "deep_group": 16, "gather_ks": 3},
 ]
 
 
 @pytest.fixture
 def restore_options():
     keys = ["scan_mode", "tile_ni", "tile_warps", "tile_ks", "tile_tail_min", "tile_band_ratio", "tile_max_scale", "chunk",
-            "gather_warps", "gather_ks", "gather_ni", "sub_batch", "lanes", "deep_group", "gather_block", "fused_smem_kb", "tile_prefetch"]
+            "gather_warps", "gather_ks", "gather_ni", "sub_batch", "lanes", "deep_group", "gather_block", "fused_smem_kb", "tile_prefetch", "deep_flat"]
     saved = {k: pigo_b200.get_option(k) for k in keys}
     yield
     for k, v in saved.items():
@@ -469,7 +471,7 @@ def test_4k_rotated_every_table_slot(gpu_face, oracle_face, frame_4k, k):
 
 @pytest.fixture
 def restore_round2_options():
-    keys = ["rot_mode", "puploc_mode", "deep_group", "gather_ks", "gather_ni", "host_first", "sub_batch", "gather_block"]
+    keys = ["rot_mode", "puploc_mode", "deep_group", "deep_flat", "gather_ks", "gather_ni", "host_stream", "copy_chunk", "sub_batch", "gather_block", "tile_warps", "scan_mode"]
     saved = {k: pigo_b200.get_option(k) for k in keys}
     yield
     for k, v in saved.items():
@@ -535,15 +537,23 @@ def test_host_frames_with_tight_stride_and_short_last_frame(gpu_face, oracle_fac
         assert cnt[f] == len(o) and out[f, :cnt[f]].tobytes() == o.tobytes()
 
 
-@pytest.mark.parametrize("host_first", [0, 2, 16])
-def test_host_group_ramp_matches_uniform_groups(gpu_face, oracle_face, restore_round2_options, host_first):
-    """Host frames are scanned in groups that ramp up (16, 48, 64, 128 by default) so that only a short first copy is
-    exposed; the result must not depend on the grouping."""
-    pigo_b200.set_option("host_first", host_first)
+@pytest.mark.parametrize("variant", [{"host_stream": 0}, {"host_stream": 1, "copy_chunk": 1, "sub_batch": 4}, {"host_stream": 1, "copy_chunk": 3},
+                                     {"host_stream": 1, "copy_chunk": 100, "deep_flat": 1}, {"host_stream": 1, "scan_mode": 3}, {"host_stream": 1, "tile_warps": 0}])
+def test_host_frames_streamed_behind_the_copy(gpu_face, oracle_face, restore_round2_options, variant):
+    """Host frames: the scan kernels start at once and wait in-kernel for each frame's copy chunk (ready counter); the result
+    must not depend on the chunking, the grouping, or on whether the polling fused kernel runs at all for the geometry."""
+    for k, v in variant.items():
+        pigo_b200.set_option(k, v)
     frames = synth.make_batch(11, 270, 480, "USF", seed0=77)
-    dets, cnt = gpu_face.RunCascadeBatch(frames, cp_of(None, 270, 480, 480, TEST_PARAMS), 0.0, cap_per_frame=128)
-    for f in range(11):
-        o = oracle_face.run_cascade(frames[f], 270, 480, 480, *TEST_PARAMS, 0.0)
+    for ang in (0.0, 0.3):
+        dets, cnt = gpu_face.RunCascadeBatch(frames, cp_of(None, 270, 480, 480, TEST_PARAMS), ang, cap_per_frame=128)
+        for f in range(11):
+            o = oracle_face.run_cascade(frames[f], 270, 480, 480, *TEST_PARAMS, ang)
+            assert cnt[f] == len(o) and dets[f, :cnt[f]].tobytes() == o.tobytes()
+    tiny = synth.make_batch(3, 30, 40, "UUU", seed0=2)      # no tileable band: the fused kernel does not run
+    dets, cnt = gpu_face.RunCascadeBatch(tiny, cp_of(None, 30, 40, 40, (20, 30, 0.1, 1.1)), 0.0, cap_per_frame=64)
+    for f in range(3):
+        o = oracle_face.run_cascade(tiny[f], 30, 40, 40, 20, 30, 0.1, 1.1, 0.0)
         assert cnt[f] == len(o) and dets[f, :cnt[f]].tobytes() == o.tobytes()
 
 

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--rows", type=int, default=1080)
     ap.add_argument("--cols", type=int, default=1920)
     ap.add_argument("--shift", type=float, default=0.2)
+    ap.add_argument("--host", action="store_true", help="also time the host API (pinned frames in, detections out) per variant")
     args = ap.parse_args()
     pigo_b200.init(0)
     clf = pigo_b200.NewPigo().Unpack(pigo_b200.load_cascade("facefinder"))
@@ -59,6 +60,27 @@ def main():
         run(); torch.cuda.synchronize()
         kt = {n: pigo_b200.get_option(f"t_{n}_ns") / 1e6 for n in ("tiled", "gather", "deep", "finalize")}
         pigo_b200.set_option("timing", 0)
+        host_ms = None
+        if args.host:
+            import ctypes as C
+            if not hasattr(main, "_pin"):
+                main._pin = torch.from_numpy(frames).pin_memory()
+                main._oh = np.zeros((args.frames, cap), dtype=pigo_b200.DET_DTYPE)
+                main._ch = np.zeros(args.frames, dtype=np.int32)
+            L = pigo_b200.lib()
+
+            def run_host():
+                rc = L.pigo_run_cascade_batch(clf._h, main._pin.data_ptr(), args.frames, args.rows * args.cols, args.rows, args.cols, args.cols, 20, 1000,
+                                              args.shift, 1.1, 0.0, main._oh.ctypes.data, cap, main._ch.ctypes.data, 0, None)
+                assert rc == 0, L.pigo_last_error()
+            run_host(); run_host()
+            hs = []
+            for _ in range(args.reps):
+                t0 = time.perf_counter(); run_host(); hs.append((time.perf_counter() - t0) * 1e3)
+            host_ms = float(np.median(hs))
+            assert int(main._ch.sum()) == int(d_cnt.sum()), "host path detections differ"
+        if host_ms is not None:
+            print(f"    host API: {host_ms:.3f} ms/step  {args.frames * W / host_ms / 1e6:.2f} Gwin/s", flush=True)
         print(f"[{v or 'default'}] frames={args.frames} {args.rows}x{args.cols} shift={args.shift}: {ms:.3f} ms/step  "
               f"{args.frames * W / ms / 1e6:.2f} Gwin/s  dets={int(d_cnt.sum())} (min {min(ts):.3f} max {max(ts):.3f}) kernels ms: "
               + " ".join(f"{k}={v:.3f}" for k, v in kt.items()), flush=True)
