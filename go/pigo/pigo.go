@@ -19,7 +19,10 @@
 //	(*PuplocCascade).RunDetector       core/puploc.go:239-277    -> pigo_puploc_run (library RNG; reference: math/rand)
 //	(*PuplocCascade).GetLandmarkPoint  core/flploc.go:36-57      -> pigo_get_landmark_point
 //	UnpackFlp, ReadCascadeDir          core/flploc.go:27-33,:60-81 (file I/O stays in Go)
-//	additive: (*Pigo).RunCascadeBatch, (*Pigo).Close, (*PuplocCascade).Close
+//	RgbToGrayscale                     core/grayscale.go:8-23    -> pigo_rgba_to_gray / pigo_ycbcr_to_nrgba (fused)
+//	GetImage, DecodeImage, ImgToNRGBA  core/image.go:13-90       -> Go decode + pigo_ycbcr_to_nrgba for *image.YCbCr (image.go)
+//	additive: (*Pigo).RunCascadeBatch, RunCascadeBatchSharded, DetectBatch, InitDevices, (*Pigo).Close, (*PuplocCascade).Close;
+//	          wire.go: the CLI's JSON wire format (cmd/pigo/main.go:88-100)
 package pigo
 
 /*
@@ -34,6 +37,7 @@ import (
 	"os"
 	"path/filepath"
 	"runtime"
+	"sync/atomic"
 	"unsafe"
 )
 
@@ -67,7 +71,23 @@ type Pigo struct {
 	h *C.pigo_cascade
 }
 
-func lastErr() error { return errors.New(C.GoString(C.pigo_last_error())) }
+// pigo_last_error() is thread-local in the library and a goroutine may migrate between OS threads between two cgo calls:
+// every failing call and the fetch of its message are therefore bracketed by runtime.LockOSThread (ADVICE round 1).
+func call(f func() C.int) (C.int, error) {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	rc := f()
+	if rc == C.PIGO_OK {
+		return rc, nil
+	}
+	return rc, errors.New(C.GoString(C.pigo_last_error()))
+}
+
+// InitDevices selects the GPUs of the *Sharded entry points (bit d of mask = device d); additive.
+func InitDevices(mask uint) error {
+	_, err := call(func() C.int { return C.pigo_init_devices(C.uint(mask)) })
+	return err
+}
 
 // NewPigo mirrors core/pigo.go:46.
 func NewPigo() *Pigo { return &Pigo{} }
@@ -79,8 +99,10 @@ func (pg *Pigo) Unpack(packet []byte) (*Pigo, error) {
 		return nil, errors.New("pigo: empty cascade packet")
 	}
 	var h *C.pigo_cascade
-	if rc := C.pigo_cascade_create((*C.uint8_t)(unsafe.Pointer(&packet[0])), C.size_t(len(packet)), &h); rc != C.PIGO_OK {
-		return nil, lastErr()
+	if _, err := call(func() C.int {
+		return C.pigo_cascade_create((*C.uint8_t)(unsafe.Pointer(&packet[0])), C.size_t(len(packet)), &h)
+	}); err != nil {
+		return nil, err
 	}
 	p := &Pigo{h: h}
 	runtime.SetFinalizer(p, func(q *Pigo) { q.Close() })
@@ -116,15 +138,17 @@ func (pg *Pigo) RunCascade(cp CascadeParams, angle float64) []Detection {
 	for {
 		buf := make([]C.pigo_det, capacity)
 		var n C.int
-		rc := C.pigo_run_cascade(pg.h, (*C.uint8_t)(unsafe.Pointer(&cp.Pixels[0])), C.int(cp.Rows), C.int(cp.Cols), C.int(cp.Dim),
-			C.int(cp.MinSize), C.int(cp.MaxSize), C.double(cp.ShiftFactor), C.double(cp.ScaleFactor), C.double(angle),
-			&buf[0], C.int(capacity), &n)
+		rc, err := call(func() C.int {
+			return C.pigo_run_cascade(pg.h, (*C.uint8_t)(unsafe.Pointer(&cp.Pixels[0])), C.int(cp.Rows), C.int(cp.Cols), C.int(cp.Dim),
+				C.int(cp.MinSize), C.int(cp.MaxSize), C.double(cp.ShiftFactor), C.double(cp.ScaleFactor), C.double(angle),
+				&buf[0], C.int(capacity), &n)
+		})
 		if rc == C.PIGO_E_CAP {
 			capacity = int(n)
 			continue
 		}
-		if rc != C.PIGO_OK {
-			panic(lastErr())
+		if err != nil {
+			panic(err)
 		}
 		return toGo(buf, int(n))
 	}
@@ -132,14 +156,23 @@ func (pg *Pigo) RunCascade(cp CascadeParams, angle float64) []Detection {
 
 // RunCascadeBatch is additive: frames of identical geometry, one []Detection per frame.
 func (pg *Pigo) RunCascadeBatch(frames [][]uint8, cp CascadeParams, angle float64) [][]Detection {
+	return pg.runBatch(frames, cp, angle, false)
+}
+
+// RunCascadeBatchSharded is RunCascadeBatch over the GPUs selected with InitDevices (frames sharded contiguously, identical result).
+func (pg *Pigo) RunCascadeBatchSharded(frames [][]uint8, cp CascadeParams, angle float64) [][]Detection {
+	return pg.runBatch(frames, cp, angle, true)
+}
+
+func (pg *Pigo) runBatch(frames [][]uint8, cp CascadeParams, angle float64, sharded bool) [][]Detection {
 	nf := len(frames)
 	if nf == 0 {
 		return nil
 	}
 	stride := cp.Rows * cp.Dim
 	var pinned unsafe.Pointer
-	if rc := C.pigo_alloc_pinned(&pinned, C.size_t(stride*nf)); rc != C.PIGO_OK {
-		panic(lastErr())
+	if _, err := call(func() C.int { return C.pigo_alloc_pinned(&pinned, C.size_t(stride*nf)) }); err != nil {
+		panic(err)
 	}
 	defer C.pigo_free_pinned(pinned)
 	host := unsafe.Slice((*uint8)(pinned), stride*nf)
@@ -150,9 +183,16 @@ func (pg *Pigo) RunCascadeBatch(frames [][]uint8, cp CascadeParams, angle float6
 	for {
 		buf := make([]C.pigo_det, capacity*nf)
 		cnt := make([]C.int, nf)
-		rc := C.pigo_run_cascade_batch(pg.h, (*C.uint8_t)(pinned), C.int(nf), C.size_t(stride), C.int(cp.Rows), C.int(cp.Cols), C.int(cp.Dim),
-			C.int(cp.MinSize), C.int(cp.MaxSize), C.double(cp.ShiftFactor), C.double(cp.ScaleFactor), C.double(angle),
-			&buf[0], C.int(capacity), &cnt[0], C.PIGO_MEM_HOST, nil)
+		rc, err := call(func() C.int {
+			if sharded {
+				return C.pigo_run_cascade_batch_sharded(pg.h, (*C.uint8_t)(pinned), C.int(nf), C.size_t(stride), C.int(cp.Rows), C.int(cp.Cols),
+					C.int(cp.Dim), C.int(cp.MinSize), C.int(cp.MaxSize), C.double(cp.ShiftFactor), C.double(cp.ScaleFactor), C.double(angle),
+					&buf[0], C.int(capacity), &cnt[0])
+			}
+			return C.pigo_run_cascade_batch(pg.h, (*C.uint8_t)(pinned), C.int(nf), C.size_t(stride), C.int(cp.Rows), C.int(cp.Cols), C.int(cp.Dim),
+				C.int(cp.MinSize), C.int(cp.MaxSize), C.double(cp.ShiftFactor), C.double(cp.ScaleFactor), C.double(angle),
+				&buf[0], C.int(capacity), &cnt[0], C.PIGO_MEM_HOST, nil)
+		})
 		if rc == C.PIGO_E_CAP {
 			for _, c := range cnt {
 				if int(c) > capacity {
@@ -161,8 +201,8 @@ func (pg *Pigo) RunCascadeBatch(frames [][]uint8, cp CascadeParams, angle float6
 			}
 			continue
 		}
-		if rc != C.PIGO_OK {
-			panic(lastErr())
+		if err != nil {
+			panic(err)
 		}
 		out := make([][]Detection, nf)
 		for i := range out {
@@ -184,8 +224,8 @@ func (pg *Pigo) ClusterDetections(detections []Detection, iouThreshold float64) 
 	}
 	out := make([]C.pigo_det, n)
 	var k C.int
-	if rc := C.pigo_cluster(&in[0], C.int(n), C.double(iouThreshold), &out[0], C.int(n), &k); rc != C.PIGO_OK {
-		panic(lastErr())
+	if _, err := call(func() C.int { return C.pigo_cluster(&in[0], C.int(n), C.double(iouThreshold), &out[0], C.int(n), &k) }); err != nil {
+		panic(err)
 	}
 	for i := range detections { // the reference sorts its argument (core/pigo.go:264)
 		detections[i] = Detection{int(in[i].row), int(in[i].col), int(in[i].scale), float32(in[i].q)}
@@ -208,10 +248,14 @@ type Puploc struct {
 // PuplocCascade mirrors core/puploc.go:23-30.
 type PuplocCascade struct {
 	h *C.pigo_puploc
-	// Seed keys the library's counter-based generator; the reference draws from the auto-seeded global math/rand
-	// (core/puploc.go:248-250) and is therefore not reproducible either.
-	Seed uint64
+	// seed keys the library's counter-based generator; the reference draws from the auto-seeded global math/rand
+	// (core/puploc.go:248-250) and is therefore not reproducible either.  Bumped atomically: RunDetector is re-entrant on a
+	// shared cascade in the reference (sync.Pool scratch, core/puploc.go:228) and stays so here.
+	seed uint64
 }
+
+// SetSeed fixes the generator key of the next RunDetector / GetLandmarkPoint calls (additive; for reproducible runs).
+func (plc *PuplocCascade) SetSeed(s uint64) { atomic.StoreUint64(&plc.seed, s) }
 
 // NewPuplocCascade mirrors core/puploc.go:33.
 func NewPuplocCascade() *PuplocCascade { return &PuplocCascade{} }
@@ -222,8 +266,10 @@ func (plc *PuplocCascade) UnpackCascade(packet []byte) (*PuplocCascade, error) {
 		return nil, errors.New("pigo: empty cascade packet")
 	}
 	var h *C.pigo_puploc
-	if rc := C.pigo_puploc_create((*C.uint8_t)(unsafe.Pointer(&packet[0])), C.size_t(len(packet)), &h); rc != C.PIGO_OK {
-		return nil, lastErr()
+	if _, err := call(func() C.int {
+		return C.pigo_puploc_create((*C.uint8_t)(unsafe.Pointer(&packet[0])), C.size_t(len(packet)), &h)
+	}); err != nil {
+		return nil, err
 	}
 	p := &PuplocCascade{h: h}
 	runtime.SetFinalizer(p, func(q *PuplocCascade) { q.Close() })
@@ -246,11 +292,12 @@ func (plc *PuplocCascade) RunDetector(pl Puploc, img ImageParams, angle float64,
 	if flipV {
 		fl = 1
 	}
-	plc.Seed++
-	rc := C.pigo_puploc_run(plc.h, &seed, 1, nil, C.uint64_t(plc.Seed), (*C.uint8_t)(unsafe.Pointer(&img.Pixels[0])),
-		C.int(img.Rows), C.int(img.Cols), C.int(img.Dim), C.double(angle), &fl, &out, C.PIGO_MEM_HOST, nil)
-	if rc != C.PIGO_OK {
-		panic(lastErr()) // e.g. Perturbs > 63: the reference panics with index out of range (core/puploc.go:261)
+	key := atomic.AddUint64(&plc.seed, 1)
+	if _, err := call(func() C.int {
+		return C.pigo_puploc_run(plc.h, &seed, 1, nil, C.uint64_t(key), (*C.uint8_t)(unsafe.Pointer(&img.Pixels[0])),
+			C.int(img.Rows), C.int(img.Cols), C.int(img.Dim), C.double(angle), &fl, &out, C.PIGO_MEM_HOST, nil)
+	}); err != nil {
+		panic(err) // e.g. Perturbs > 63: the reference panics with index out of range (core/puploc.go:261)
 	}
 	return &Puploc{Row: int(out.row), Col: int(out.col), Scale: float32(out.scale)}
 }
@@ -264,11 +311,12 @@ func (plc *PuplocCascade) GetLandmarkPoint(leftEye, rightEye *Puploc, img ImageP
 	if flipV {
 		fl = 1
 	}
-	plc.Seed++
-	rc := C.pigo_get_landmark_point(plc.h, &le, &re, (*C.uint8_t)(unsafe.Pointer(&img.Pixels[0])), C.int(img.Rows), C.int(img.Cols),
-		C.int(img.Dim), C.int(perturb), fl, nil, C.uint64_t(plc.Seed), &out)
-	if rc != C.PIGO_OK {
-		panic(lastErr())
+	key := atomic.AddUint64(&plc.seed, 1)
+	if _, err := call(func() C.int {
+		return C.pigo_get_landmark_point(plc.h, &le, &re, (*C.uint8_t)(unsafe.Pointer(&img.Pixels[0])), C.int(img.Rows), C.int(img.Cols),
+			C.int(img.Dim), C.int(perturb), fl, nil, C.uint64_t(key), &out)
+	}); err != nil {
+		panic(err)
 	}
 	return &Puploc{Row: int(out.row), Col: int(out.col), Scale: float32(out.scale)}
 }

@@ -6,10 +6,9 @@
 // rejecting one are wasted work, acceptable because windows that reach this kernel usually live long.
 // Bit-exactness: each lane produces the same leaf the serial walk would, and the sum is formed in the same order.
 //
-// Round 2: (1) the loop is FLAT -- every iteration each lane group either fetches its next window or walks one step, so the
-// 32/GROUP groups of a warp never wait for each other at a reconvergence point (round 1 nested "fetch { while (alive) step }",
-// ncu: 16.6 of 32 lanes active per instruction); (2) ROT variant: classifyRotatedRegion (core/pigo.go:150-191) with the
-// node's sample offsets read from the per-call table (RotNode, common.cuh) instead of being recomputed per node.
+// Round 2: (1) queue items carry their ladder entry, so the consumer needs no binary search; (2) ROT variant:
+// classifyRotatedRegion (core/pigo.go:150-191) with the node's sample offsets read from the per-call table (RotNode,
+// common.cuh) instead of being recomputed per node; (3) a flat-loop variant (deep_flat=1), measured and left off.
 #include "common.cuh"
 #include "host.h"
 
@@ -62,11 +61,80 @@ __device__ __forceinline__ float deep_walk(const ScanArgs& A, const FaceTables& 
   }
 }
 
-// FLAT = 1: every iteration each lane group either fetches its next window or walks one step (no group waits for another
-// at a reconvergence point, but a fetch of one group delays the step of the others).  FLAT = 0: round-1 structure, the
-// groups of a warp fetch together and the warp stays in the step loop until its slowest window is done.
-template <int GROUP, int ROT, int FLAT>
+// Decodes a queue item: window geometry from the ladder entry the producer packed (0xffff = not known: search).
+struct DeepWin {
+  uint32_t wid;
+  int frame, t0, s, r, c;
+  float acc;
+  const uint8_t* pc;
+  const RotNode* rt;
+};
+template <int ROT>
+__device__ __forceinline__ DeepWin deep_fetch(const ScanArgs& A, const FaceTables& T, unsigned long long g) {
+  const DeepItem it = A.longq[g];
+  int si = (int)(it.frame_si >> 16);
+  if (si == 0xffff) si = find_scale(A.plan, A.nscales, it.wid);
+  const ScaleEntry e = A.plan[si];
+  const uint32_t local = it.wid - e.wbase;
+  const uint32_t ri = local / (uint32_t)e.ncols, ci = local - ri * (uint32_t)e.ncols;
+  DeepWin w;
+  w.s = e.s; w.wid = it.wid; w.frame = (int)(it.frame_si & 0xffffu); w.t0 = it.tree; w.acc = it.acc;
+  w.r = e.off + (int)ri * e.step; w.c = e.off + (int)ci * e.step;
+  w.pc = A.frames + (size_t)w.frame * A.frame_stride;
+  w.rt = A.rot_tab;
+  if (ROT) w.rt = A.rot_tab + (size_t)si * T.ntrees * 64;
+  else w.pc += (size_t)w.r * A.dim + w.c;
+  return w;
+}
+
+// Round-1 loop structure: the lane groups of a warp fetch together, then the warp stays in the step loop until its slowest
+// window is done (measured faster than the flat loop below: one fetch latency per 32/GROUP windows instead of one per window).
+template <int GROUP, int ROT>
 __global__ void __launch_bounds__(256) deep_kernel(const ScanArgs A, unsigned long long* counter) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (GROUP - 1);
+  const unsigned gmask = GROUP == 32 ? 0xffffffffu : (GROUP == 16 ? (0xffffu << (lane & 16)) : (0xffu << (lane & 24)));
+  const int leader = lane & ~(GROUP - 1);
+  const FaceTables T = A.tab;
+  const uint32_t qn = min(*A.long_count, A.long_cap);
+  const int lim = A.rows - 1;
+  for (;;) {
+    unsigned long long g = 0;
+    if (sub == 0) g = atomicAdd(counter, 1ull);
+    g = __shfl_sync(gmask, g, leader);
+    if (g >= qn) break;
+    const DeepWin w = deep_fetch<ROT>(A, T, g);
+    int t0 = w.t0;
+    float acc = w.acc;
+    bool rejected = false;
+    float thr_prev = 0.f;
+    while (t0 < T.ntrees && !rejected) {
+      const int t = min(t0 + sub, T.ntrees - 1);      // lanes past the last tree redo it harmlessly
+      const float thr = __ldg(T.thresh + t);
+      const float pred = deep_walk<ROT>(A, T, w.pc, w.rt, t, w.r, w.c, w.s, lim);
+      const int nvalid = min(GROUP, T.ntrees - t0);
+      for (int j = 0; j < nvalid; ++j) {              // the reference's sequential accumulation, :137-141
+        acc += __shfl_sync(gmask, pred, leader + j);
+        thr_prev = __shfl_sync(gmask, thr, leader + j);
+        if (acc <= thr_prev) { rejected = true; break; }
+      }
+      t0 += GROUP;
+    }
+    if (!rejected && sub == 0) {
+      const float q = acc - thr_prev;                 // :144 (thr_prev == threshold of the last tree)
+      if (q > 0.0f) {                                 // :246
+        const int pos = atomicAdd(A.raw_count + w.frame, 1);
+        if (pos < A.cap) A.raw[(size_t)w.frame * A.cap + pos] = RawDet{w.wid, q};
+      }
+    }
+  }
+}
+
+// Flat loop (option deep_flat=1): every iteration each lane group either fetches its next window or walks one step.  No group
+// waits for another at a reconvergence point (ncu round 1: 16.6 of 32 lanes active per instruction in the nested loop), but
+// every fetch now delays the step of the three other groups; measured 3 % slower on the bench workload, kept as a variant.
+template <int GROUP, int ROT>
+__global__ void __launch_bounds__(256) deep_flat_kernel(const ScanArgs A, unsigned long long* counter) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int sub = lane & (GROUP - 1);
@@ -75,73 +143,58 @@ __global__ void __launch_bounds__(256) deep_kernel(const ScanArgs A, unsigned lo
   const FaceTables T = A.tab;
   const uint32_t qn = min(*A.long_count, A.long_cap);
   const int lim = A.rows - 1;
-
   bool have = false, more = true;
-  uint32_t wid = 0;
-  int frame = 0, t0 = 0, s = 0, r = 0, c = 0;
-  float acc = 0.f;
-  const uint8_t* pc = A.frames;        // unrotated: the window's centre pixel; rotated: the frame
-  const RotNode* rt = A.rot_tab;       // rotated: this scale's node table, tree 0
-
+  DeepWin w{};
+  w.pc = A.frames; w.rt = A.rot_tab;
   for (;;) {
     if (!have && more) {
       unsigned long long g = 0;
       if (sub == 0) g = atomicAdd(counter, 1ull);
       g = __shfl_sync(gmask, g, leader);
-      if (g >= qn) {
-        more = false;
-      } else {
-        const DeepItem it = A.longq[g];
-        const int si = (int)(it.frame_si >> 16);       // ladder entry, packed by the producer (no search here)
-        const ScaleEntry e = A.plan[si];
-        const uint32_t local = it.wid - e.wbase;
-        const uint32_t ri = local / (uint32_t)e.ncols, ci = local - ri * (uint32_t)e.ncols;
-        s = e.s; wid = it.wid; frame = (int)(it.frame_si & 0xffffu); t0 = it.tree; acc = it.acc;
-        r = e.off + (int)ri * e.step; c = e.off + (int)ci * e.step;
-        pc = A.frames + (size_t)frame * A.frame_stride;
-        if (ROT) rt = A.rot_tab + (size_t)si * T.ntrees * 64;
-        else pc += (size_t)r * A.dim + c;
-        have = true;
-      }
+      if (g >= qn) more = false;
+      else { w = deep_fetch<ROT>(A, T, g); have = true; }
     }
-    if (FLAT ? !__any_sync(FULL, have) : !have) break;   // FLAT = 0: a group without work leaves; the others carry on
-    bool looping = have;
-    while (looping) {
-      const int t = min(t0 + sub, T.ntrees - 1);        // lanes past the last tree redo it harmlessly
+    if (!__any_sync(FULL, have)) break;
+    if (have) {
+      const int t = min(w.t0 + sub, T.ntrees - 1);
       const float thr = __ldg(T.thresh + t);
-      const float pred = deep_walk<ROT>(A, T, pc, rt, t, r, c, s, lim);
-      // the reference's sequential accumulation, core/pigo.go:137-141
-      const int nvalid = min(GROUP, T.ntrees - t0);
+      const float pred = deep_walk<ROT>(A, T, w.pc, w.rt, t, w.r, w.c, w.s, lim);
+      const int nvalid = min(GROUP, T.ntrees - w.t0);
       bool rejected = false;
       float thr_last = 0.f;
       for (int j = 0; j < nvalid; ++j) {
-        acc += __shfl_sync(gmask, pred, leader + j);
+        w.acc += __shfl_sync(gmask, pred, leader + j);
         thr_last = __shfl_sync(gmask, thr, leader + j);
-        if (acc <= thr_last) { rejected = true; break; }
+        if (w.acc <= thr_last) { rejected = true; break; }
       }
-      t0 += GROUP;
+      w.t0 += GROUP;
       if (rejected) {
         have = false;
-      } else if (t0 >= T.ntrees) {
+      } else if (w.t0 >= T.ntrees) {
         if (sub == 0) {
-          const float q = acc - thr_last;               // :144 (thr_last == threshold of the last tree)
-          if (q > 0.0f) {                               // :246
-            const int pos = atomicAdd(A.raw_count + frame, 1);
-            if (pos < A.cap) A.raw[(size_t)frame * A.cap + pos] = RawDet{wid, q};
+          const float q = w.acc - thr_last;
+          if (q > 0.0f) {
+            const int pos = atomicAdd(A.raw_count + w.frame, 1);
+            if (pos < A.cap) A.raw[(size_t)w.frame * A.cap + pos] = RawDet{w.wid, q};
           }
         }
         have = false;
       }
-      looping = FLAT ? false : have;                    // FLAT: one step per outer iteration
     }
   }
 }
 
 template <int ROT, int FLAT>
 static void launch_deep_g(const ScanArgs& A, unsigned long long* counter, int grid, int group, cudaStream_t st) {
-  if (group == 8) deep_kernel<8, ROT, FLAT><<<grid, 256, 0, st>>>(A, counter);
-  else if (group == 16) deep_kernel<16, ROT, FLAT><<<grid, 256, 0, st>>>(A, counter);
-  else deep_kernel<32, ROT, FLAT><<<grid, 256, 0, st>>>(A, counter);
+  if (FLAT) {
+    if (group == 8) deep_flat_kernel<8, ROT><<<grid, 256, 0, st>>>(A, counter);
+    else if (group == 16) deep_flat_kernel<16, ROT><<<grid, 256, 0, st>>>(A, counter);
+    else deep_flat_kernel<32, ROT><<<grid, 256, 0, st>>>(A, counter);
+  } else {
+    if (group == 8) deep_kernel<8, ROT><<<grid, 256, 0, st>>>(A, counter);
+    else if (group == 16) deep_kernel<16, ROT><<<grid, 256, 0, st>>>(A, counter);
+    else deep_kernel<32, ROT><<<grid, 256, 0, st>>>(A, counter);
+  }
 }
 
 void launch_deep(const ScanArgs& A, unsigned long long* counter, int grid, int group, cudaStream_t st) {

@@ -53,7 +53,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-constexpr uint32_t kCascOff = 384;  // mbarriers live in the first 384 bytes of shared memory
+constexpr uint32_t kCascOff = 384;  // mbarriers live in the first 272 bytes of shared memory, then the scale lookup table
+// Window size -> ladder entry, for the queue items of the tile warps (their lanes carry the size, not the index): one byte per
+// size < kLutSizes in the control region; 0xff / larger sizes = unknown, the consumer searches the ladder (find_scale).
+constexpr uint32_t kLutOff = 272;
+constexpr int kLutSizes = 112;
+__device__ __forceinline__ int scale_index_of(const uint8_t* smem, int s) {
+  const unsigned v = (unsigned)s < (unsigned)kLutSizes ? smem[kLutOff + s] : 0xffu;
+  return v == 0xffu ? 0xffff : (int)v;
+}
 __device__ __forceinline__ int ceil_div_pos(int num, int den) { return num <= 0 ? 0 : (num + den - 1) / den; }
 
 
@@ -179,7 +187,9 @@ __device__ __forceinline__ void gather_role(const TiledArgs& A, const uint8_t* s
           const uint32_t k = cur + rank;
           if (from_q1) {
             const DeepItem it = S.deep[k];
-            const int si = (int)(it.frame_si >> 16), itf = (int)(it.frame_si & 0xffffu);
+            int si = (int)(it.frame_si >> 16);
+            const int itf = (int)(it.frame_si & 0xffffu);
+            if (si == 0xffff) si = find_scale(S.plan, S.nscales, it.wid);   // producer did not know the ladder entry
             const ScaleEntry e = S.plan[si];
             const uint32_t local = it.wid - e.wbase;
             const uint32_t ri = local / (uint32_t)e.ncols, ci = local - ri * (uint32_t)e.ncols;
@@ -348,7 +358,13 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
 
   // ---- stage the cascade prefix with the TMA bulk engine (one elected thread issues, all threads wait)
   if (lane == 0 && warp < A.tile_warps) mbar_init(wbar, 1);
+  if (threadIdx.x < kLutSizes) smem[kLutOff + threadIdx.x] = 0xff;
   stage_cascade(A, smem_base, casc, (casc_bytes + 15u) & ~15u);
+  if ((int)threadIdx.x < A.scan.nscales && threadIdx.x < 255) {
+    const int sz = A.scan.plan[threadIdx.x].s;
+    if (sz >= 0 && sz < kLutSizes) smem[kLutOff + sz] = (uint8_t)threadIdx.x;     // sizes are distinct along the ladder
+  }
+  __syncthreads();
 
   const ScanArgs& S = A.scan;
   if (warp >= A.tile_warps) {   // warp-specialised: the remaining warps scan the large scales by global-memory gathers
@@ -495,9 +511,7 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
               if (lane == 0) qbase = atomicAdd(S.deep_count, (unsigned)__popc(live));
               qbase = __shfl_sync(FULL, qbase, 0);
               const unsigned pos = qbase + __popc(live & lanemask_lt());
-              int qsi = B.scale_lo;                 // ladder entry of this lane's window: lane k of the warp describes band scale k
-              for (int k = 0; k < B.nscales; ++k)
-                if (__shfl_sync(FULL, e.s, k) == sv[u]) qsi = B.scale_lo + k;
+              const int qsi = scale_index_of(smem, sv[u]);
               if (alive[u] && pos < S.deep_cap) {
                 S.deep[pos] = DeepItem{wid[u], pack_frame_si(frame, qsi), (int)((tbo[u] - casc) / kTreeRec), acc[u]};
                 alive[u] = false;
@@ -604,9 +618,7 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
               qbase = __shfl_sync(FULL, qbase, 0);
               const unsigned pos = qbase + __popc(mb & lanemask_lt());
               bool failed = false;
-              int qsi = B.scale_lo;
-              for (int k = 0; k < B.nscales; ++k)
-                if (__shfl_sync(FULL, e.s, k) == sv[u]) qsi = B.scale_lo + k;
+              const int qsi = scale_index_of(smem, sv[u]);
               if (at_end) {
                 if (pos < S.long_cap) {
                   S.longq[pos] = DeepItem{wid[u], pack_frame_si(frame, qsi), A.ks, acc[u]};

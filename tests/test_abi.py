@@ -125,10 +125,46 @@ def test_go_shim_calls_match_the_header():
     header = open(os.path.join(root, "include", "pigo_b200.h")).read()
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
     protos = dict(_calls(header, ""))
-    go = open(os.path.join(root, "go", "pigo", "pigo.go")).read()
+    import glob
+    go = "\n".join(open(f).read() for f in sorted(glob.glob(os.path.join(root, "go", "pigo", "*.go"))))
     go = re.sub(r"//[^\n]*", "", go)
     calls = _calls(go, "C.")
-    assert len(calls) >= 10
+    assert len(calls) >= 16
+    for needed in ("pigo_rgba_to_gray", "pigo_ycbcr_to_nrgba", "pigo_detect_batch", "pigo_detect_batch_sharded", "pigo_run_cascade_batch_sharded",
+                   "pigo_init_devices"):
+        assert needed in dict(calls), f"the Go shim does not bind {needed}"
     for name, nargs in calls:
         assert name in protos, f"{name} is not declared in pigo_b200.h"
         assert nargs == protos[name], f"{name}: Go passes {nargs} arguments, the header declares {protos[name]}"
+
+
+def test_go_shim_exports_what_the_reference_callers_use():
+    """cmd/pigo/main.go:288-353 and the examples call pigo.GetImage, pigo.RgbToGrayscale, NewPigo, Unpack, RunCascade,
+    ClusterDetections, NewPuplocCascade, UnpackCascade, RunDetector, ReadCascadeDir, GetLandmarkPoint: the shim package must
+    export each of them (compile-drop-in), plus the additive entry points."""
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    go = "\n".join(open(f).read() for f in sorted(glob.glob(os.path.join(root, "go", "pigo", "*.go"))))
+    funcs = set(re.findall(r"^func (?:\([^)]*\) )?([A-Z][A-Za-z0-9]*)\(", go, flags=re.M))
+    types = set(re.findall(r"^type ([A-Z][A-Za-z0-9]*) ", go, flags=re.M))
+    for name in ("GetImage", "DecodeImage", "ImgToNRGBA", "RgbToGrayscale", "NewPigo", "Unpack", "RunCascade", "ClusterDetections", "NewPuplocCascade",
+                 "UnpackCascade", "UnpackFlp", "RunDetector", "ReadCascadeDir", "GetLandmarkPoint", "RunCascadeBatch", "RunCascadeBatchSharded",
+                 "DetectBatch", "InitDevices", "WireDetections"):
+        assert name in funcs, name
+    for name in ("CascadeParams", "ImageParams", "Detection", "Pigo", "Puploc", "PuplocCascade", "FlpCascade", "Coord", "DetectionJSON"):
+        assert name in types, name
+    assert "plc.Seed++" not in go and "atomic.AddUint64(&plc.seed, 1)" in go      # re-entrant like the reference (sync.Pool scratch)
+    assert go.count("runtime.LockOSThread()") >= 1                                # thread-local error message fetched on the failing thread
+
+
+def test_cli_json_wire_format():
+    """pigo_b200/wire.py == the `pigo -json` output format (cmd/pigo/main.go:88-100): x/y swap, omitempty, accumulating points, Q > 5."""
+    from pigo_b200 import Puploc, wire
+    from pigo_b200.pipeline import Face
+    f1 = Face((100, 200, 80, 7.5), Puploc(90, 180, 20.9, 0), Puploc(91, 0, 20.0, 0), [Puploc(120, 190, 3.7, 0), Puploc(0, 5, 1.0, 0)])
+    f2 = Face((300, 40, 81, 5.0))                                            # Q == 5.0 is NOT > qThresh
+    f3 = Face((50, 40, 80, 9.0))                                             # no refinements (e.g. Scale <= 50 path): inherits the points
+    got = wire.marshal_wire([f1, f2, f3])
+    assert got == ('[{"eyes":[{"x":180,"y":90,"size":20}],"landmark_points":[{"x":190,"y":120,"size":3}],"face":{"x":160,"y":60,"size":80}},'
+                   '{"eyes":[{"x":180,"y":90,"size":20}],"landmark_points":[{"x":190,"y":120,"size":3}],"face":{"y":10,"size":80}}]')
+    assert wire.marshal_wire([]) == "[]"
