@@ -48,6 +48,17 @@ def main():
             clf.run_cascade_batch_device(d.data_ptr(), nf, R * C, R, C, C, *PRM, ang, d_out.data_ptr(), cap, d_cnt.data_ptr(), st)
             torch.cuda.synchronize()
         print(mode, "detections", int(d_cnt.sum()))
+    elif mode == "pipe2":
+        # the device-sequenced pipeline (pigo_detect_batch) on 64 class-F 1080p frames, 2 calls
+        plc = pigo_b200.NewPuplocCascade().UnpackCascade(pigo_b200.load_cascade("puploc"))
+        names = sorted(set(pipeline.EYE_CASCADES + pipeline.MOUTH_CASCADES))
+        flp = {n: pigo_b200.NewPuplocCascade().UnpackCascade(pigo_b200.load_cascade("lps/" + n)) for n in names}
+        fr = np.stack([synth.frame_faces(None, 1080, 1920, shift=(37 * i, 53 * i), noise_seed=100 + i) for i in range(64)])
+        cp = CascadeParams(ImageParams(None, 1080, 1920, 1920), *PRM)
+        df = pigo_b200.DeviceFrames(fr)
+        for _ in range(2):
+            faces, nfaces, points = pipeline.detect_batch_device(clf, plc, flp, df, cp, eye_perturbs=63, raw=True)
+        print("pipe2 faces", int((faces["scale"] > 50).sum()))
     elif mode == "pipe":
         plc = pigo_b200.NewPuplocCascade().UnpackCascade(pigo_b200.load_cascade("puploc"))
         names = sorted(set(pipeline.EYE_CASCADES + pipeline.MOUTH_CASCADES))
