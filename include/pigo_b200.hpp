@@ -14,6 +14,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "pigo_b200.h"
@@ -81,12 +82,32 @@ class Pigo {                    // core/pigo.go:37-43
     for (int i = 0; i < k; ++i) res[i] = Detection{out[i].row, out[i].col, out[i].scale, out[i].q};
     return res;
   }
+  // additive: RunCascade for a frame batch (host frames `stride` bytes apart); sharded = over the GPUs of InitDevices
+  std::vector<std::vector<Detection>> RunCascadeBatch(const uint8_t* frames, int nframes, size_t stride, const CascadeParams& cp, double angle,
+                                                      bool sharded = false) const {
+    int cap = 256;
+    for (;;) {
+      std::vector<pigo_det> buf((size_t)cap * nframes);
+      std::vector<int> cnt((size_t)nframes);
+      const int rc = sharded ? pigo_run_cascade_batch_sharded(h_.get(), frames, nframes, stride, cp.Image.Rows, cp.Image.Cols, cp.Image.Dim, cp.MinSize,
+                                                              cp.MaxSize, cp.ShiftFactor, cp.ScaleFactor, angle, buf.data(), cap, cnt.data())
+                           : pigo_run_cascade_batch(h_.get(), frames, nframes, stride, cp.Image.Rows, cp.Image.Cols, cp.Image.Dim, cp.MinSize, cp.MaxSize,
+                                                    cp.ShiftFactor, cp.ScaleFactor, angle, buf.data(), cap, cnt.data(), PIGO_MEM_HOST, nullptr);
+      if (rc == PIGO_E_CAP) { for (int c : cnt) cap = c > cap ? c : cap; continue; }
+      check(rc);
+      std::vector<std::vector<Detection>> out((size_t)nframes);
+      for (int f = 0; f < nframes; ++f)
+        for (int i = 0; i < cnt[f]; ++i) { const pigo_det& d = buf[(size_t)f * cap + i]; out[f].push_back(Detection{d.row, d.col, d.scale, d.q}); }
+      return out;
+    }
+  }
   const pigo_cascade* handle() const { return h_.get(); }
 
  private:
   std::shared_ptr<pigo_cascade> h_;
 };
 inline Pigo NewPigo() { return Pigo(); }   // core/pigo.go:46
+inline void InitDevices(unsigned mask) { check(pigo_init_devices(mask)); }   // additive: GPUs of the sharded entry points
 
 class PuplocCascade {            // core/puploc.go:23-30
  public:
@@ -120,10 +141,55 @@ class PuplocCascade {            // core/puploc.go:23-30
     check(pigo_get_landmark_point(h_.get(), &le, &re, img.Pixels, img.Rows, img.Cols, img.Dim, perturb, flipV ? 1 : 0, randoms, ++Seed, &out));
     return Puploc{out.row, out.col, out.scale, 0};
   }
+  const pigo_puploc* handle() const { return h_.get(); }
 
  private:
   std::shared_ptr<pigo_puploc> h_;
 };
+
+// additive: the face -> cluster -> pupils -> landmarks sequence of core/flploc_test.go:75-154 / cmd/pigo/main.go:369-565 for a frame
+// batch in one library call (sequenced on the device); calls[c] = (landmark cascade, flipV).
+struct FaceResult {
+  Detection Face;
+  bool Refined = false;          // Scale > min_face_scale: eyes and landmarks below are valid
+  Puploc LeftEye, RightEye;
+  std::vector<Puploc> Landmarks;
+};
+inline std::vector<std::vector<FaceResult>> DetectBatch(const Pigo& face, const PuplocCascade& plc,
+                                                        const std::vector<std::pair<const PuplocCascade*, bool>>& calls, const uint8_t* frames,
+                                                        int nframes, size_t stride, const CascadeParams& cp, double iou, int min_face_scale,
+                                                        int eye_perturbs, int flp_perturbs, uint64_t rng_seed, bool sharded = false,
+                                                        const float* randoms = nullptr, int face_cap = 32) {
+  const int ncalls = (int)calls.size();
+  std::vector<const pigo_puploc*> hs;
+  std::vector<uint8_t> fl;
+  for (auto& c : calls) { hs.push_back(c.first->handle()); fl.push_back(c.second ? 1 : 0); }
+  pigo_pipeline_params prm{};
+  prm.min_size = cp.MinSize; prm.max_size = cp.MaxSize; prm.shift_factor = cp.ShiftFactor; prm.scale_factor = cp.ScaleFactor; prm.angle = 0.0;
+  prm.iou_threshold = iou; prm.min_face_scale = min_face_scale; prm.eye_perturbs = eye_perturbs; prm.flp_perturbs = flp_perturbs; prm.det_cap = 0;
+  std::vector<pigo_det> faces((size_t)nframes * face_cap);
+  std::vector<int> nfaces((size_t)nframes);
+  std::vector<pigo_point> pts((size_t)nframes * face_cap * (2 + ncalls));
+  check(sharded ? pigo_detect_batch_sharded(face.handle(), plc.handle(), hs.data(), fl.data(), ncalls, frames, nframes, stride, cp.Image.Rows, cp.Image.Cols,
+                                            cp.Image.Dim, &prm, randoms, rng_seed, faces.data(), face_cap, nfaces.data(), pts.data())
+                : pigo_detect_batch(face.handle(), plc.handle(), hs.data(), fl.data(), ncalls, frames, nframes, stride, cp.Image.Rows, cp.Image.Cols,
+                                    cp.Image.Dim, &prm, randoms, rng_seed, faces.data(), face_cap, nfaces.data(), pts.data(), PIGO_MEM_HOST, nullptr));
+  std::vector<std::vector<FaceResult>> out((size_t)nframes);
+  for (int f = 0; f < nframes; ++f)
+    for (int k = 0; k < nfaces[f]; ++k) {
+      const pigo_det& d = faces[(size_t)f * face_cap + k];
+      FaceResult r;
+      r.Face = Detection{d.row, d.col, d.scale, d.q};
+      if (d.scale > min_face_scale) {
+        const pigo_point* p = &pts[((size_t)f * face_cap + k) * (2 + ncalls)];
+        r.Refined = true;
+        r.LeftEye = Puploc{p[0].row, p[0].col, p[0].scale, 0}; r.RightEye = Puploc{p[1].row, p[1].col, p[1].scale, 0};
+        for (int c = 0; c < ncalls; ++c) r.Landmarks.push_back(Puploc{p[2 + c].row, p[2 + c].col, p[2 + c].scale, 0});
+      }
+      out[f].push_back(r);
+    }
+  return out;
+}
 inline PuplocCascade NewPuplocCascade() { return PuplocCascade(); }   // core/puploc.go:33
 
 }  // namespace pigo

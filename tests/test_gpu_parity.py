@@ -695,3 +695,21 @@ def test_ycbcr_to_nrgba_matches_oracle(subsample):
         exp = O.ycbcr_to_nrgba(y, cb, cr, subsample, w, h, mx, my)
         assert np.array_equal(got, exp)
         assert np.array_equal(gray, O.rgba_to_gray(exp))
+
+
+def test_cpp_sharded_over_every_visible_device():
+    """tests/cpp/test_sharded.cpp: one process drives every visible GPU through include/pigo_b200.h (pigo_init_devices,
+    pigo_run_cascade_batch_sharded, pigo_detect_batch_sharded) and requires byte-identical results to the 1-GPU calls.
+    With one GPU this exercises the same code with a single shard; run under `gpurun --gpus 2` it is the 2-device test."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "test_sharded")
+    if not os.path.exists(exe):
+        import __graft_entry__
+        __graft_entry__.build()
+    r = subprocess.run([exe, root], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "== single device" in r.stdout
+    need = int(os.environ.get("PIGO_REQUIRE_DEVICES", "1"))
+    assert int(r.stdout.split("devices=")[1].split()[0]) >= need
