@@ -188,8 +188,12 @@ PuplocReplica* puploc_replica(pigo_puploc* p, int dev, int* rc) {
   if ((*rc = use_device(dev))) return nullptr;
   PuplocReplica* r = new PuplocReplica();
   r->device = dev; r->num_sms = device_sms(dev);
-  if ((*rc = r->codes.reserve(p->h_codes.size())) || (*rc = r->preds.reserve(p->h_preds.size() * 4))) { delete r; return nullptr; }
-  cudaMemcpy(r->codes.p, p->h_codes.data(), p->h_codes.size(), cudaMemcpyHostToDevice);
+  // device layout of the codes: one pad word in front of every tree (see PuplocTables)
+  const size_t nt = (size_t)p->stages * p->trees, ncode = 4 * (size_t)p->leaves - 4;
+  std::vector<int8_t> padded(nt * (ncode + 4) + 16, 0);
+  for (size_t t = 0; t < nt; ++t) memcpy(padded.data() + t * (ncode + 4) + 4, p->h_codes.data() + t * ncode, ncode);
+  if ((*rc = r->codes.reserve(padded.size())) || (*rc = r->preds.reserve(p->h_preds.size() * 4))) { delete r; return nullptr; }
+  cudaMemcpy(r->codes.p, padded.data(), padded.size(), cudaMemcpyHostToDevice);
   cudaError_t e = cudaMemcpy(r->preds.p, p->h_preds.data(), p->h_preds.size() * 4, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { delete r; *rc = set_err(PIGO_E_CUDA, "table upload failed: %s", cudaGetErrorString(e)); return nullptr; }
   r->tab.codes = (const int8_t*)r->codes.p; r->tab.preds = (const float*)r->preds.p;

@@ -82,7 +82,8 @@ struct Options {
 extern Options g_opt;
 
 struct PuplocTables {
-  const int8_t* codes;  // [stages*trees][4*leaves-4]
+  const int8_t* codes;  // [stages*trees][4*leaves]: 4 pad bytes, then the reference's 4*leaves-4 code bytes (core/puploc.go:75-80), so that node i
+                        // sits at word i+1 and its two children (nodes 2i+1, 2i+2) at the 8-byte aligned word pair 2i+2, 2i+3
   const float* preds;   // [stages*trees][leaves][2]
   int32_t stages, trees, depth, leaves;
   float scales;

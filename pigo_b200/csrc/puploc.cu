@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(1024, 1) puploc_kernel(PuplocTables T, const p
   const int P = seed.perturbs;
   const bool flip = flipv_arr ? (flipv_arr[sidx] != 0) : false;
   const int L = T.leaves;
-  const int tree_codes = 4 * L - 4;
+  const int tree_codes = 4 * L;   // device layout: one pad word, then the 4L-4 code bytes (node i at word i+1), see PuplocTables
 
   for (int i = warp; i < 63; i += 32) {       // warp-uniform: perturbation i (pool slot i)
     float r = 0.f, c = 0.f, s = 0.f;
@@ -81,11 +81,11 @@ __global__ void __launch_bounds__(1024, 1) puploc_kernel(PuplocTables T, const p
           const int* tc = reinterpret_cast<const int*>(T.codes + tg * tree_codes);   // 4-byte aligned: tree_codes % 4 == 0
           const float2* tp = reinterpret_cast<const float2*>(T.preds + tg * 2 * L);
           int idx = 0;
-          int cw = __ldg(tc);
+          int cw = __ldg(tc + 1);
           for (int k = 0; k < T.depth; ++k) {
-            // children of node idx are nodes 2idx+1, 2idx+2: fetch both while this node's pixels are in flight
+            // children of node idx are nodes 2idx+1, 2idx+2 = words 2idx+2, 2idx+3: one aligned 64-bit load, in flight with this node's pixels
             int kl = 0, kr = 0;
-            if (k + 1 < T.depth) { kl = __ldg(tc + 2 * idx + 1); kr = __ldg(tc + 2 * idx + 2); }
+            if (k + 1 < T.depth) { const int2 kk = __ldg(reinterpret_cast<const int2*>(tc) + idx + 1); kl = kk.x; kr = kk.y; }
             const int k0 = (int8_t)(cw), k2 = (int8_t)(cw >> 16);
             const int k1 = flip ? neg_i8((int8_t)(cw >> 8)) : (int)(int8_t)(cw >> 8);
             const int k3 = flip ? neg_i8(cw >> 24) : (cw >> 24);
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupW
     const bool flip = W.flipv ? (W.flipv[slot] != 0) : (W.flip_of[j] != 0);
     const int frame = W.slots_per_frame > 0 ? slot / W.slots_per_frame : (W.slot_frame ? W.slot_frame[slot] : 0);
     const uint8_t* __restrict__ pixels = W.frames + (size_t)frame * W.frame_stride;
-    const int L = T.leaves, tree_codes = 4 * L - 4, rlim = W.nrows - 1, clim = W.ncols - 1;
+    const int L = T.leaves, tree_codes = 4 * L, rlim = W.nrows - 1, clim = W.ncols - 1;   // padded device layout, see PuplocTables
     const bool rot = W.rot_slot >= 0;
 
     if (tid < 64) {
@@ -218,15 +218,17 @@ __global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupW
         const int i = p / T.trees, t = p - i * T.trees;
         const int ir = s_ir[i], ic = s_ic[i], rs = s_rs[i];
         const size_t tg = (size_t)st * T.trees + t;
-        const int* tc = reinterpret_cast<const int*>(T.codes + tg * tree_codes);      // tree_codes % 4 == 0
+        const int* tc = reinterpret_cast<const int*>(T.codes + tg * tree_codes);
+        const int2* tc2 = reinterpret_cast<const int2*>(tc);
         const float2* tp = reinterpret_cast<const float2*>(T.preds + tg * 2 * L);
         int idx = 0;
-        int cw = __ldg(tc);
+        int cw = __ldg(tc + 1);
         if (!rot) {
           for (int k = 0; k < T.depth; ++k) {
-            // children of node idx are nodes 2idx+1, 2idx+2: fetched while this node's pixels are in flight
+            // children of node idx are nodes 2idx+1, 2idx+2 = words 2idx+2, 2idx+3 of the padded tree: ONE aligned 64-bit
+            // load, in flight together with this node's pixels
             int kl = 0, kr = 0;
-            if (k + 1 < T.depth) { kl = __ldg(tc + 2 * idx + 1); kr = __ldg(tc + 2 * idx + 2); }
+            if (k + 1 < T.depth) { const int2 kk = __ldg(tc2 + idx + 1); kl = kk.x; kr = kk.y; }
             const int k0 = (int8_t)(cw), k2 = (int8_t)(cw >> 16);
             const int k1 = flip ? neg_i8((int8_t)(cw >> 8)) : (int)(int8_t)(cw >> 8);
             const int k3 = flip ? neg_i8(cw >> 24) : (cw >> 24);
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupW
           const long long iqs = s_qs[i], iqc = s_qc[i];        // 64-bit products: int(256*s)*code leaves 32 bits for s > 2^15
           for (int k = 0; k < T.depth; ++k) {
             int kl = 0, kr = 0;
-            if (k + 1 < T.depth) { kl = __ldg(tc + 2 * idx + 1); kr = __ldg(tc + 2 * idx + 2); }
+            if (k + 1 < T.depth) { const int2 kk = __ldg(tc2 + idx + 1); kl = kk.x; kr = kk.y; }
             const int k0 = (int8_t)(cw), k2 = (int8_t)(cw >> 16);
             const int k1 = flip ? neg_i8((int8_t)(cw >> 8)) : (int)(int8_t)(cw >> 8);
             const int k3 = flip ? neg_i8(cw >> 24) : (cw >> 24);

@@ -59,6 +59,18 @@ def main():
         for _ in range(2):
             faces, nfaces, points = pipeline.detect_batch_device(clf, plc, flp, df, cp, eye_perturbs=63, raw=True)
         print("pipe2 faces", int((faces["scale"] > 50).sum()))
+    elif mode == "gray":
+        npx = 16 * 1080 * 1920
+        rgba = torch.randint(0, 256, (npx, 4), dtype=torch.uint8, device="cuda")
+        gray = torch.empty(npx, dtype=torch.uint8, device="cuda")
+        yy = torch.randint(0, 256, (16 * 1080, 1920), dtype=torch.uint8, device="cuda")
+        cb = torch.randint(0, 256, (16 * 540, 960), dtype=torch.uint8, device="cuda")
+        cr = torch.randint(0, 256, (16 * 540, 960), dtype=torch.uint8, device="cuda")
+        out = torch.empty((npx, 4), dtype=torch.uint8, device="cuda")
+        for _ in range(2):
+            pigo_b200.lib().pigo_rgba_to_gray(rgba.data_ptr(), npx, gray.data_ptr(), 3, st)
+            pigo_b200.lib().pigo_ycbcr_to_nrgba(yy.data_ptr(), cb.data_ptr(), cr.data_ptr(), 1920, 960, 2, 0, 0, 1920, 16 * 1080, out.data_ptr(), gray.data_ptr(), 3, st)
+            torch.cuda.synchronize()
     elif mode == "pipe":
         plc = pigo_b200.NewPuplocCascade().UnpackCascade(pigo_b200.load_cascade("puploc"))
         names = sorted(set(pipeline.EYE_CASCADES + pipeline.MOUTH_CASCADES))
