@@ -254,7 +254,9 @@ static std::vector<int> group_schedule(int nframes, bool streamed) {
 // ---- RunCascade on one device -----------------------------------------------------------------------------------
 static int scan_batch_on(pigo_cascade* c, int dev, const uint8_t* frames, int nframes, size_t frame_stride, int rows, int cols, int dim,
                          int min_size, int max_size, double shift_factor, double scale_factor, double angle, pigo_det* out,
-                         int cap_per_frame, int* n_out, unsigned flags, void* stream_) {
+                         int cap_per_frame, int* n_out, unsigned flags, void* stream_, uint8_t* host_frames_dst = nullptr) {
+  // host_frames_dst (optional, host frames only): device buffer of nframes * round256(rows*dim) bytes that receives the
+  // frames instead of the call's own scratch -- the pipeline keeps them for the pupil / landmark stages that follow.
   int rc = PIGO_OK;
   FaceReplica* R = face_replica(c, dev, &rc);
   if (!R) return rc;
@@ -289,10 +291,14 @@ static int scan_batch_on(pigo_cascade* c, int dev, const uint8_t* frames, int nf
   const size_t frame_bytes = (size_t)rows * dim;
   const size_t frame_min = rows > 0 ? (size_t)(rows - 1) * dim + cols : 0;
   size_t d_stride = frame_stride;
+  uint8_t* d_frames_w = host_frames_dst;
   if (!frames_dev) {
     d_stride = (frame_bytes + 255) & ~(size_t)255;
-    if ((rc = w->frames.reserve(d_stride * nframes + 256))) return rc;
-    d_frames = (const uint8_t*)w->frames.p;
+    if (!d_frames_w) {
+      if ((rc = w->frames.reserve(d_stride * nframes + 256))) return rc;
+      d_frames_w = (uint8_t*)w->frames.p;
+    }
+    d_frames = d_frames_w;
   }
   pigo_det* d_out = out;
   int32_t* d_nout = n_out;
@@ -359,7 +365,7 @@ static int scan_batch_on(pigo_cascade* c, int dev, const uint8_t* frames, int nf
       const long long chunk = streamed ? std::max<long long>(1, g_opt.copy_chunk.load()) : nf;
       for (int c0 = 0; c0 < nf; c0 += (int)chunk) {
         const int cn = (int)std::min<long long>(chunk, nf - c0);
-        uint8_t* dst = (uint8_t*)w->frames.p + (size_t)(f0 + c0) * d_stride;
+        uint8_t* dst = d_frames_w + (size_t)(f0 + c0) * d_stride;
         const uint8_t* src = frames + (size_t)(f0 + c0) * frame_stride;
         const bool last = f0 + c0 + cn == nframes;   // only the batch's last frame may be short; the others have a successor behind them
         if (frame_stride == d_stride || cn == 1) {
@@ -930,16 +936,11 @@ static int detect_batch_on(int dev, pigo_cascade* face, pigo_puploc* puploc, pig
   const uint8_t* d_frames = frames;
   size_t d_stride = frame_stride;
   if (!frames_dev) {
-    // all frames go up first (the pupil / landmark stages gather from them later); the copy is cut in pieces so that the
-    // scan of the first group does not wait for the whole batch
+    // the scan call below streams the host frames into THIS buffer (chunked copy overlapped with the scan kernels); the
+    // pupil / landmark stages gather from it afterwards
     d_stride = (frame_bytes + 255) & ~(size_t)255;
     if ((rc = w->frames.reserve(d_stride * nframes + 256))) return rc;
     d_frames = (const uint8_t*)w->frames.p;
-    const size_t frame_min = (size_t)(rows - 1) * dim + cols;
-    if (frame_stride == d_stride || nframes == 1)
-      CUDA_TRY(cudaMemcpyAsync(w->frames.p, frames, d_stride * (size_t)(nframes - 1) + frame_min, cudaMemcpyHostToDevice, st));
-    else
-      CUDA_TRY(cudaMemcpy2DAsync(w->frames.p, d_stride, frames, frame_stride, frame_min, nframes, cudaMemcpyHostToDevice, st));
   }
   const size_t nslots = (size_t)nframes * face_cap * stride;
   // scratch: raw detections + counts, clusters + counts, seeds, points, faces, work counters
@@ -965,8 +966,12 @@ static int detect_batch_on(int dev, pigo_cascade* face, pigo_puploc* puploc, pig
   CUDA_TRY(cudaMemsetAsync(w->counters.p, 0, 256, st));
   CUDA_TRY(cudaMemsetAsync(d_points, 0, b_pts, st));
 
-  rc = scan_batch_on(face, dev, d_frames, nframes, d_stride, rows, cols, dim, P.min_size, P.max_size, P.shift_factor, P.scale_factor, P.angle,
-                     d_dets, det_cap, d_cnt, PIGO_FRAMES_DEVICE | PIGO_OUT_DEVICE, st);
+  if (frames_dev)
+    rc = scan_batch_on(face, dev, d_frames, nframes, d_stride, rows, cols, dim, P.min_size, P.max_size, P.shift_factor, P.scale_factor, P.angle,
+                       d_dets, det_cap, d_cnt, PIGO_FRAMES_DEVICE | PIGO_OUT_DEVICE, st);
+  else
+    rc = scan_batch_on(face, dev, frames, nframes, frame_stride, rows, cols, dim, P.min_size, P.max_size, P.shift_factor, P.scale_factor, P.angle,
+                       d_dets, det_cap, d_cnt, PIGO_OUT_DEVICE, st, (uint8_t*)w->frames.p);
   if (rc) return rc;
   rc = cluster_batch_on(dev, d_dets, d_cnt, nframes, det_cap, P.iou_threshold, d_clusters, face_cap, d_ncl, PIGO_OUT_DEVICE, st);
   if (rc) return rc;

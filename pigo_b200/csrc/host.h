@@ -45,6 +45,7 @@ struct Options {
   std::atomic<long long> copy_chunk{8};     // host_stream: frames per H2D copy chunk
   std::atomic<long long> deep_flat{0};      // deep kernel loop: 0 = groups of a warp fetch together (round 1), 1 = flat (fetch or step per iteration)
   std::atomic<long long> rot_mode{0};       // rotated scan: 0 = table-driven block kernel + deep kernel, 1 = universal gather kernel
+  std::atomic<long long> puploc_stage{1};   // pair kernel: 1 = the current stage's node codes are staged in shared memory
   std::atomic<long long> puploc_mode{0};    // RunDetector kernel: 0 = (perturbation, tree)-pair kernel, 1 = warp-per-perturbation kernel
   std::atomic<long long> lanes{1};          // internal streams the groups alternate between
   std::atomic<long long> tile_tail_min{6};  // tail policy threshold
@@ -61,7 +62,7 @@ struct Options {
          {"gather_block", &Options::gather_block}, {"deep_group", &Options::deep_group},
         {"sub_batch", &Options::sub_batch}, {"lanes", &Options::lanes}, {"tile_tail_min", &Options::tile_tail_min},
         {"tile_band_ratio", &Options::tile_band_ratio}, {"timing", &Options::timing}, {"host_stream", &Options::host_stream}, {"copy_chunk", &Options::copy_chunk},
-        {"deep_flat", &Options::deep_flat}, {"rot_mode", &Options::rot_mode}, {"puploc_mode", &Options::puploc_mode}};
+        {"deep_flat", &Options::deep_flat}, {"rot_mode", &Options::rot_mode}, {"puploc_mode", &Options::puploc_mode}, {"puploc_stage", &Options::puploc_stage}};
     for (const Entry& e : table)
       if (k == e.name) return &(this->*e.field);
     return nullptr;

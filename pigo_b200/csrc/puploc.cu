@@ -5,6 +5,8 @@
 //
 // float32 arithmetic uses explicit round-to-nearest intrinsics (and the library is built with
 // -fmad=false): Go on amd64 never fuses r += dr*s (core/puploc.go:149-151).
+#include <algorithm>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -160,8 +162,16 @@ constexpr int kPairThreads = 512;
 // rejects larger scales) cannot wrap: anything beyond +-2^30 clamps to the same image border as the exact value would
 __device__ __forceinline__ int clamp_coord(float v) { return max(-(1 << 30), min(1 << 30, (int)v)); }
 
-__global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupWork W, unsigned int* __restrict__ counter) {
-  extern __shared__ float2 s_leaf[];     // [63][trees]
+// STAGED: the node codes of the CURRENT STAGE (trees x 4L bytes: 40 KB for a landmark cascade, 80 KB for the pupil cascade)
+// are copied to shared memory with coalesced loads before the stage's walks, so that the per-level child fetch is a
+// shared-memory load instead of a lane-divergent global one (ncu round 2, unstaged: L1TEX 71 % busy at 25 sectors per
+// request, issue 47 %); the shared copy skews consecutive trees by 8 bytes, otherwise every tree's node i would sit in the
+// same bank.  The pixel pairs stay global gathers (a landmark seed's patch is up to ~100 KB).
+template <bool STAGED>
+__global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupWork W, unsigned int* __restrict__ counter, int leaf_bytes) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  float2* s_leaf = reinterpret_cast<float2*>(s_dyn);     // [63][trees]
+  uint8_t* s_codes = s_dyn + leaf_bytes;                 // STAGED: [trees][4L + 8]
   __shared__ float s_r[64], s_c[64], s_s[64];
   __shared__ int s_ir[64], s_ic[64], s_rs[64], s_qs[64], s_qc[64];
   __shared__ unsigned s_item;
@@ -183,6 +193,16 @@ __global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupW
     const uint8_t* __restrict__ pixels = W.frames + (size_t)frame * W.frame_stride;
     const int L = T.leaves, tree_codes = 4 * L, rlim = W.nrows - 1, clim = W.ncols - 1;   // padded device layout, see PuplocTables
     const bool rot = W.rot_slot >= 0;
+    const int sstride = tree_codes + 8;                    // shared-memory tree stride (bank skew)
+    auto stage_codes = [&](int st) {
+      const uint2* src = reinterpret_cast<const uint2*>(T.codes + (size_t)st * T.trees * tree_codes);
+      const int per_tree = tree_codes / 8, total = per_tree * T.trees;
+      for (int q = tid; q < total; q += nt) {
+        const int t = q / per_tree, o = q - t * per_tree;
+        *reinterpret_cast<uint2*>(s_codes + t * sstride + 8 * o) = __ldg(src + q);
+      }
+    };
+    if (STAGED) stage_codes(0);
 
     if (tid < 64) {
       float r = 0.f, c = 0.f, s = 0.f;
@@ -218,17 +238,17 @@ __global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupW
         const int i = p / T.trees, t = p - i * T.trees;
         const int ir = s_ir[i], ic = s_ic[i], rs = s_rs[i];
         const size_t tg = (size_t)st * T.trees + t;
-        const int* tc = reinterpret_cast<const int*>(T.codes + tg * tree_codes);
+        const int* tc = STAGED ? reinterpret_cast<const int*>(s_codes + t * sstride) : reinterpret_cast<const int*>(T.codes + tg * tree_codes);
         const int2* tc2 = reinterpret_cast<const int2*>(tc);
         const float2* tp = reinterpret_cast<const float2*>(T.preds + tg * 2 * L);
         int idx = 0;
-        int cw = __ldg(tc + 1);
+        int cw = STAGED ? tc[1] : __ldg(tc + 1);
         if (!rot) {
           for (int k = 0; k < T.depth; ++k) {
             // children of node idx are nodes 2idx+1, 2idx+2 = words 2idx+2, 2idx+3 of the padded tree: ONE aligned 64-bit
             // load, in flight together with this node's pixels
             int kl = 0, kr = 0;
-            if (k + 1 < T.depth) { const int2 kk = __ldg(tc2 + idx + 1); kl = kk.x; kr = kk.y; }
+            if (k + 1 < T.depth) { const int2 kk = STAGED ? tc2[idx + 1] : __ldg(tc2 + idx + 1); kl = kk.x; kr = kk.y; }
             const int k0 = (int8_t)(cw), k2 = (int8_t)(cw >> 16);
             const int k1 = flip ? neg_i8((int8_t)(cw >> 8)) : (int)(int8_t)(cw >> 8);
             const int k3 = flip ? neg_i8(cw >> 24) : (cw >> 24);
@@ -242,7 +262,7 @@ __global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupW
           const long long iqs = s_qs[i], iqc = s_qc[i];        // 64-bit products: int(256*s)*code leaves 32 bits for s > 2^15
           for (int k = 0; k < T.depth; ++k) {
             int kl = 0, kr = 0;
-            if (k + 1 < T.depth) { const int2 kk = __ldg(tc2 + idx + 1); kl = kk.x; kr = kk.y; }
+            if (k + 1 < T.depth) { const int2 kk = STAGED ? tc2[idx + 1] : __ldg(tc2 + idx + 1); kl = kk.x; kr = kk.y; }
             const int k0 = (int8_t)(cw), k2 = (int8_t)(cw >> 16);
             const int k1 = flip ? neg_i8((int8_t)(cw >> 8)) : (int)(int8_t)(cw >> 8);
             const int k3 = flip ? neg_i8(cw >> 24) : (cw >> 24);
@@ -258,6 +278,7 @@ __global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupW
         s_leaf[p] = __ldg(tp + (idx - (L - 1)));
       }
       __syncthreads();
+      if (STAGED && st + 1 < T.stages) stage_codes(st + 1);   // the sums below only read s_leaf
       if (tid < P) {
         float dr = 0.f, dc = 0.f;
         const float2* lf = s_leaf + tid * T.trees;
@@ -295,16 +316,22 @@ __global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupW
 int launch_puploc_pairs(const PupWork& W, unsigned int* counter, int num_sms, cudaStream_t st) {
   int trees_max = 0;
   for (int i = 0; i < W.ntabs; ++i) trees_max = max(trees_max, W.tab[i].trees);
-  const size_t smem = (size_t)63 * trees_max * sizeof(float2);
-  if (smem > 160 * 1024) return -1;                                   // caller falls back to the warp-per-perturbation kernel
+  size_t codes_max = 0;
+  for (int i = 0; i < W.ntabs; ++i) codes_max = std::max(codes_max, (size_t)W.tab[i].trees * (4 * (size_t)W.tab[i].leaves + 8));
+  const size_t leaf = ((size_t)63 * trees_max * sizeof(float2) + 15) & ~(size_t)15;
+  if (leaf > 100 * 1024) return -1;                                   // caller falls back to the warp-per-perturbation kernel
+  const bool staged = g_opt.puploc_stage.load() != 0 && leaf + codes_max <= 110 * 1024;   // two CTAs per SM at least
+  const size_t smem = leaf + (staged ? codes_max : 0);
   static bool attr_set[kMaxDevices] = {};
   int dev = 0; cudaGetDevice(&dev);
-  if (smem > 48 * 1024 && !attr_set[dev]) {
-    cudaFuncSetAttribute(puploc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  if (!attr_set[dev]) {
+    cudaFuncSetAttribute(puploc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaFuncSetAttribute(puploc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
     attr_set[dev] = true;
   }
   const int grid = max(1, min(W.nwork, num_sms * 3));
-  puploc_pair_kernel<<<grid, kPairThreads, smem, st>>>(W, counter);
+  if (staged) puploc_pair_kernel<true><<<grid, kPairThreads, smem, st>>>(W, counter, (int)leaf);
+  else puploc_pair_kernel<false><<<grid, kPairThreads, smem, st>>>(W, counter, (int)leaf);
   return 0;
 }
 

@@ -471,7 +471,7 @@ def test_4k_rotated_every_table_slot(gpu_face, oracle_face, frame_4k, k):
 
 @pytest.fixture
 def restore_round2_options():
-    keys = ["rot_mode", "puploc_mode", "deep_group", "deep_flat", "gather_ks", "gather_ni", "host_stream", "copy_chunk", "sub_batch", "gather_block", "tile_warps", "scan_mode"]
+    keys = ["rot_mode", "puploc_mode", "puploc_stage", "deep_group", "deep_flat", "gather_ks", "gather_ni", "host_stream", "copy_chunk", "sub_batch", "gather_block", "tile_warps", "scan_mode"]
     saved = {k: pigo_b200.get_option(k) for k in keys}
     yield
     for k, v in saved.items():
@@ -557,11 +557,12 @@ def test_host_frames_streamed_behind_the_copy(gpu_face, oracle_face, restore_rou
         assert cnt[f] == len(o) and dets[f, :cnt[f]].tobytes() == o.tobytes()
 
 
-@pytest.mark.parametrize("mode", [0, 1])
-def test_puploc_kernels_agree_with_oracle(sample_gray, restore_round2_options, mode):
+@pytest.mark.parametrize("mode,stage", [(0, 1), (0, 0), (1, 0)])
+def test_puploc_kernels_agree_with_oracle(sample_gray, restore_round2_options, mode, stage):
     """Both RunDetector kernels ((perturbation, tree)-pair kernel and warp-per-perturbation kernel), rotated and not,
     flips, Perturbs 0..63, seeds near and beyond the image border, on a frame batch."""
     pigo_b200.set_option("puploc_mode", mode)
+    pigo_b200.set_option("puploc_stage", stage)
     rng = np.random.default_rng(123)
     frames = np.stack([sample_gray, np.roll(sample_gray, 13, axis=1), 255 - sample_gray])
     for pkname in ("puploc", "lps/lp93"):
