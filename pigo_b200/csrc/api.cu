@@ -1112,6 +1112,7 @@ int pigo_ycbcr_to_nrgba(const uint8_t* y, const uint8_t* cb, const uint8_t* cr, 
   if (min_x < 0 || min_y < 0) return set_err(PIGO_E_INVALID, "negative rectangle origin");
   const size_t npix = (size_t)width * height;
   if (npix == 0) return ensure_device();
+  if (npix > 0x7fffffffull) return set_err(PIGO_E_INVALID, "images larger than 2^31 pixels are not supported");
   if (!y || !cb || !cr || (!nrgba && !gray)) return set_err(PIGO_E_INVALID, "null argument");
   int rc = ensure_device();
   if (rc) return rc;

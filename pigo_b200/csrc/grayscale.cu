@@ -52,31 +52,52 @@ void launch_gray(const uint8_t* rgba, size_t npix, uint8_t* gray, int grid, cuda
 // make the round trip through HBM when only the detector's input is wanted.
 __device__ __forceinline__ uint32_t sat16(int v) { return (uint32_t)v & 0xff000000u ? (uint32_t)(~(v >> 31)) & 0xffu : (uint32_t)(v >> 16); }
 
+// One thread converts 4 consecutive pixels of a row (32-bit index arithmetic, one 16-byte store for the NRGBA output).
 __global__ void __launch_bounds__(256) ycbcr_kernel(const uint8_t* __restrict__ yp, const uint8_t* __restrict__ cbp, const uint8_t* __restrict__ crp,
                                                     int y_stride, int c_stride, int sub, int min_x, int min_y, int width, int height,
-                                                    uint32_t* __restrict__ nrgba, uint8_t* __restrict__ gray) {
-  const size_t npix = (size_t)width * height;
+                                                    uint32_t* __restrict__ nrgba, uint8_t* __restrict__ gray, int vec_ok) {
   const int xs = (sub == 1 || sub == 2) ? 1 : ((sub == 4 || sub == 5) ? 2 : 0);   // chroma x shift: 422/420 halve, 411/410 quarter
   const int ys = (sub == 2 || sub == 3 || sub == 5) ? 1 : 0;                       // chroma y shift: 420/440/410 halve
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
-    const int dy = (int)(i / width), dx = (int)(i - (size_t)dy * width);
-    const int sx = min_x + dx, sy = min_y + dy;                                   // image.go:66-67
-    const size_t siy = (size_t)dy * y_stride + dx;                                // YOffset: (y-Rect.Min.Y)*YStride + (x-Rect.Min.X)
-    const size_t sic = (size_t)((sy >> ys) - (min_y >> ys)) * c_stride + ((sx >> xs) - (min_x >> xs));   // COffset
-    const int yy1 = (int)__ldg(yp + siy) * 0x10101, cb1 = (int)__ldg(cbp + sic) - 128, cr1 = (int)__ldg(crp + sic) - 128;
-    const uint32_t r = sat16(yy1 + 91881 * cr1), gg = sat16(yy1 - 22554 * cb1 - 46802 * cr1), b = sat16(yy1 + 116130 * cb1);
-    const uint32_t px = r | (gg << 8) | (b << 16) | 0xff000000u;
-    if (nrgba) nrgba[i] = px;
-    if (gray) gray[i] = (uint8_t)luma(px);
+  const unsigned chunks = (unsigned)(width + 3) >> 2;
+  const unsigned total = chunks * (unsigned)height;                                // < 2^31: width * height < 2^31 is checked by the host
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+    const int dy = (int)(q / chunks), dx0 = (int)(q - (unsigned)dy * chunks) * 4;
+    const int sy = min_y + dy;                                                     // image.go:66-67
+    const uint8_t* yrow = yp + (size_t)dy * y_stride;                             // YOffset: (y-Rect.Min.Y)*YStride + (x-Rect.Min.X)
+    const size_t crow = (size_t)((sy >> ys) - (min_y >> ys)) * c_stride;          // COffset row
+    uint32_t px[4], lum = 0;
+    const int n = min(4, width - dx0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      px[k] = 0;
+      if (k < n) {
+        const int dx = dx0 + k;
+        const size_t sic = crow + (size_t)(((min_x + dx) >> xs) - (min_x >> xs));
+        const int yy1 = (int)__ldg(yrow + dx) * 0x10101, cb1 = (int)__ldg(cbp + sic) - 128, cr1 = (int)__ldg(crp + sic) - 128;
+        const uint32_t r = sat16(yy1 + 91881 * cr1), gg = sat16(yy1 - 22554 * cb1 - 46802 * cr1), b = sat16(yy1 + 116130 * cb1);
+        px[k] = r | (gg << 8) | (b << 16) | 0xff000000u;
+        if (gray) lum |= luma(px[k]) << (8 * k);
+      }
+    }
+    const size_t o = (size_t)dy * width + dx0;
+    if (nrgba) {
+      if (vec_ok && n == 4) *reinterpret_cast<uint4*>(nrgba + o) = make_uint4(px[0], px[1], px[2], px[3]);
+      else for (int k = 0; k < n; ++k) nrgba[o + k] = px[k];
+    }
+    if (gray) {
+      if (vec_ok && n == 4) *reinterpret_cast<uint32_t*>(gray + o) = lum;
+      else for (int k = 0; k < n; ++k) gray[o + k] = (uint8_t)(lum >> (8 * k));
+    }
   }
 }
 
 void launch_ycbcr(const uint8_t* y, const uint8_t* cb, const uint8_t* cr, int y_stride, int c_stride, int subsample, int min_x, int min_y,
                   int width, int height, uint8_t* nrgba, uint8_t* gray, int grid, cudaStream_t st) {
-  const size_t npix = (size_t)width * height;
-  const size_t want = (npix + 255) / 256;
+  const size_t want = ((size_t)((width + 3) / 4) * height + 255) / 256;
+  // vector stores need width % 4 == 0 (every row chunk starts at a multiple of 4 pixels) and aligned outputs
+  const int vec_ok = (width % 4 == 0) && (((uintptr_t)nrgba) % 16 == 0) && (((uintptr_t)gray) % 4 == 0);
   ycbcr_kernel<<<(int)std::max<size_t>(1, std::min<size_t>(want, (size_t)grid)), 256, 0, st>>>(y, cb, cr, y_stride, c_stride, subsample, min_x, min_y, width,
-                                                                                             height, reinterpret_cast<uint32_t*>(nrgba), gray);
+                                                                                             height, reinterpret_cast<uint32_t*>(nrgba), gray, vec_ok);
 }
 
 }  // namespace pigo

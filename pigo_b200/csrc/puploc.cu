@@ -314,10 +314,14 @@ __global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupW
 }
 
 int launch_puploc_pairs(const PupWork& W, unsigned int* counter, int num_sms, cudaStream_t st) {
+  // shared memory is sized by the cascades THIS launch uses (positions first .. first+span-1), not by every table of the work list
   int trees_max = 0;
-  for (int i = 0; i < W.ntabs; ++i) trees_max = max(trees_max, W.tab[i].trees);
   size_t codes_max = 0;
-  for (int i = 0; i < W.ntabs; ++i) codes_max = std::max(codes_max, (size_t)W.tab[i].trees * (4 * (size_t)W.tab[i].leaves + 8));
+  for (int j = 0; j < W.span && j < 32; ++j) {
+    const PuplocTables& T = W.tab[W.tab_of[j]];
+    trees_max = max(trees_max, T.trees);
+    codes_max = std::max(codes_max, (size_t)T.trees * (4 * (size_t)T.leaves + 8));
+  }
   const size_t leaf = ((size_t)63 * trees_max * sizeof(float2) + 15) & ~(size_t)15;
   if (leaf > 100 * 1024) return -1;                                   // caller falls back to the warp-per-perturbation kernel
   const bool staged = g_opt.puploc_stage.load() != 0 && leaf + codes_max <= 110 * 1024;   // two CTAs per SM at least
