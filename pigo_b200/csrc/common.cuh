@@ -115,6 +115,11 @@ constexpr int kTiledMaxThreads = 1024;
 // level -- leaves) can be fetched with one aligned 64-bit load; 130 words skew consecutive trees by two banks.
 constexpr int kTreeRec = 520;
 constexpr int kMaxBands = 4;
+// dense-head kernel: entries of the per-warp survivor ring (12 bytes each), ladder entries with a head table, head trees
+constexpr int kRing = 48;
+constexpr int kRingEntry = 12;
+constexpr int kHeadMaxScales = 16;
+constexpr int kHeadTreesMax = 4;
 
 // A band = consecutive ladder entries [scale_lo, scale_lo+nscales) served by one family of pixel tiles.
 struct TileBand {
@@ -149,6 +154,13 @@ struct TiledArgs {
   int32_t tile_prefetch;                  // tile role: fetch both children of a node with one 64-bit load
   int32_t consume_q1;                     // gather-v2 only: drain the straggler queue Q1 (complete at launch)
   int32_t gather_ni;                      // windows per lane in the gather role (ILP)
+  // dense-head variant of the tile role (scan_head_kernel): the first `head_trees` trees of every tiled ladder entry have a
+  // per-scale node table (two precomputed 16-bit sample offsets per node) at shared-memory offset head_off; survivors of the
+  // head travel through a per-warp ring (ring_off, kRing entries of 12 bytes) to the generic lane-refill loop
+  int32_t head_trees;                     // 0 = classic kernel
+  int32_t head_nscales;                   // ladder entries [0, head_nscales) are tiled
+  uint32_t head_off, ring_off, tiles_off;
+  int32_t head_back;                      // generic phase: with an empty ring and fewer live lanes than this, park them in the ring and go back to the head
 };
 
 __device__ __constant__ int c_qcos[33] = {256, 251, 236, 212, 181, 142, 97, 49, 0, -49, -97, -142, -181, -212, -236, -251, -256,

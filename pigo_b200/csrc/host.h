@@ -43,6 +43,8 @@ struct Options {
   std::atomic<long long> host_stream{1};    // host frames: 1 = the scan kernels start at once and wait IN-KERNEL for each frame's copy (a ready counter the copy
                                             // stream bumps after every chunk), so copy and scan overlap frame by frame; 0 = per-group copy events (round 1)
   std::atomic<long long> copy_chunk{8};     // host_stream: frames per H2D copy chunk
+  std::atomic<long long> tile_head{0};      // fused kernel, tile role: 0 = classic lane refill from tree 0, N = dense head over the first N trees (scan_head_kernel)
+  std::atomic<long long> head_back{12};     // dense head: generic phase parks its live windows and returns to the head below this many live lanes
   std::atomic<long long> deep_flat{0};      // deep kernel loop: 0 = groups of a warp fetch together (round 1), 1 = flat (fetch or step per iteration)
   std::atomic<long long> rot_mode{0};       // rotated scan: 0 = table-driven block kernel + deep kernel, 1 = universal gather kernel
   std::atomic<long long> puploc_stage{1};   // pair kernel: 1 = the current stage's node codes are staged in shared memory
@@ -62,7 +64,7 @@ struct Options {
          {"gather_block", &Options::gather_block}, {"deep_group", &Options::deep_group},
         {"sub_batch", &Options::sub_batch}, {"lanes", &Options::lanes}, {"tile_tail_min", &Options::tile_tail_min},
         {"tile_band_ratio", &Options::tile_band_ratio}, {"timing", &Options::timing}, {"host_stream", &Options::host_stream}, {"copy_chunk", &Options::copy_chunk},
-        {"deep_flat", &Options::deep_flat}, {"rot_mode", &Options::rot_mode}, {"puploc_mode", &Options::puploc_mode}, {"puploc_stage", &Options::puploc_stage}};
+        {"deep_flat", &Options::deep_flat}, {"tile_head", &Options::tile_head}, {"head_back", &Options::head_back}, {"rot_mode", &Options::rot_mode}, {"puploc_mode", &Options::puploc_mode}, {"puploc_stage", &Options::puploc_stage}};
     for (const Entry& e : table)
       if (k == e.name) return &(this->*e.field);
     return nullptr;

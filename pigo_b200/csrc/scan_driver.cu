@@ -97,13 +97,15 @@ static TilePlan plan_bands(const std::vector<ScaleEntry>& plan, uint32_t tile_by
 // Shared-memory layout of the fused kernel: mbarriers (384 B) | cascade prefix | per-warp tiles (128-byte aligned).
 struct FusedLayout {
   bool ok = false;
-  size_t tiles_off = 0;
+  size_t tiles_off = 0, head_off = 0, ring_off = 0;
   uint32_t tile_bytes = 0;
 };
-static FusedLayout fused_layout(int W, int ks, size_t smem_cap_req) {
+static FusedLayout fused_layout(int W, int ks, size_t smem_cap_req, int head_trees = 0) {
   FusedLayout L;
   const size_t casc_bytes = ((size_t)ks * kTreeRec + 15) & ~(size_t)15;   // TMA bulk copies move multiples of 16 bytes
-  L.tiles_off = (384 + casc_bytes + 127) & ~(size_t)127;
+  L.head_off = 384 + casc_bytes;
+  L.ring_off = L.head_off + (size_t)(head_trees > 0 ? kHeadMaxScales * head_trees * 256 : 0);
+  L.tiles_off = (L.ring_off + (size_t)(head_trees > 0 ? W * kRing * kRingEntry : 0) + 127) & ~(size_t)127;
   if (W <= 0 || L.tiles_off + 4096 * (size_t)W >= kSmemPerCta) return L;
   // fused_smem_kb < 227 leaves the rest of the SM's 256 KB to L1 (which the gather warps' pixel loads live in)
   size_t smem_cap = kSmemPerCta;
@@ -119,6 +121,7 @@ struct FusedPlan {
   FusedLayout L;
   TilePlan tp;
   int W = 0, ks = 0, ni = 1;
+  int head = 0;   // trees of the dense head (0 = classic tile role)
 };
 static FusedPlan plan_fused(const std::vector<ScaleEntry>& plan, int ntrees) {
   FusedPlan P;
@@ -129,10 +132,28 @@ static FusedPlan plan_fused(const std::vector<ScaleEntry>& plan, int ntrees) {
   P.ks = (int)std::min<long long>(std::min<long long>(std::max<long long>(1, g_opt.tile_ks.load()), ntrees), fit);
   int max_scale = (int)g_opt.tile_max_scale.load();
   if (max_scale <= 0) max_scale = 1 << 30;
-  P.L = fused_layout(P.W, P.ks, (size_t)std::max<long long>(0, g_opt.fused_smem_kb.load()) * 1024);
-  if (P.L.ok)
-    P.tp = plan_bands(plan, P.L.tile_bytes, max_scale, (int)std::max<long long>(100, g_opt.tile_band_ratio.load()),
-                      (int)std::max<long long>(16, g_opt.tile_min_core.load()), (int)std::max<long long>(1, g_opt.tile_min_core_steps.load()));
+  // dense head: needs its tables and rings in shared memory (a fixed reservation for kHeadMaxScales ladder entries), NI = 1,
+  // a resident prefix longer than the head and short enough for the 6-bit tree field of a ring entry
+  P.head = (int)std::min<long long>(std::max<long long>(0, g_opt.tile_head.load()), kHeadTreesMax);
+  if (P.ni != 1 || P.ks <= P.head || P.ks > 63 || g_opt.tile_prefetch.load()) P.head = 0;
+  auto plan_with = [&](int head) {
+    P.L = fused_layout(P.W, P.ks, (size_t)std::max<long long>(0, g_opt.fused_smem_kb.load()) * 1024, head);
+    P.tp = TilePlan();
+    if (P.L.ok)
+      P.tp = plan_bands(plan, P.L.tile_bytes, max_scale, (int)std::max<long long>(100, g_opt.tile_band_ratio.load()),
+                        (int)std::max<long long>(16, g_opt.tile_min_core.load()), (int)std::max<long long>(1, g_opt.tile_min_core_steps.load()));
+  };
+  plan_with(P.head);
+  if (P.head > 0) {
+    // every tiled ladder entry needs a head table; its window size must fit the ring entry's 8-bit field and its offsets int16
+    bool ok = P.L.ok && P.tp.nbands > 0 && P.tp.first_untiled <= kHeadMaxScales;
+    for (int b = 0; ok && b < P.tp.nbands; ++b) {
+      const TileBand& B = P.tp.band[b];
+      if ((long long)(B.halo_lo + 1) * (B.pitch + 1) >= 32768) ok = false;
+      if (plan[B.scale_lo + B.nscales - 1].s > 255) ok = false;
+    }
+    if (!ok) { P.head = 0; plan_with(0); }
+  }
   return P;
 }
 
@@ -282,6 +303,9 @@ int run_scan(FaceReplica* c, Workspace* w, int lane, ScanArgs& A, unsigned long 
       F.total_tiles = (unsigned long long)tp.tiles_per_frame * A.nframes;
       F.tile_warps = W;
       F.consume_q1 = 0;
+      F.head_trees = P.head; F.head_nscales = tp.first_untiled;
+      F.head_off = (uint32_t)P.L.head_off; F.ring_off = (uint32_t)P.L.ring_off; F.tiles_off = (uint32_t)P.L.tiles_off;
+      F.head_back = (int)std::min<long long>(std::max<long long>(1, g_opt.head_back.load()), kRing - 32);
       first_untiled = tp.first_untiled;
       if (Wg > 0 && first_untiled < A.nscales) {
         if ((rc = upload_block_prefix(w, first_untiled, A.nscales, T.gb_shift, st, &F.gather_blocks_per_frame))) return rc;

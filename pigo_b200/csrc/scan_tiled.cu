@@ -670,6 +670,325 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
   }
 }
 
+// =============================================================================================================
+// Dense-head variant of the fused kernel (round 2).  Same warp specialisation, same tiles, same queues; the tile role is
+// split in two phases so that the first trees -- tree 0 and 1 are 63 % of all tree walks, and every window walks tree 0 --
+// run on a cheaper instruction stream:
+//   HEAD  : the warp takes 32 consecutive fresh windows of ONE scale and walks trees 0..head_trees-1 in lock-step.  All lanes
+//           are on the same tree and scale, so a node is one word of a per-scale table holding the two precomputed sample
+//           offsets (dr*pitch + dc as int16): a level is LDS, 2 x (extract, add), 2 x LDS.U8, compare, index = 11
+//           instructions instead of 21, there is no per-lane tree / scale state and no refill bookkeeping per walk.
+//           Lanes whose window was rejected idle until the batch ends (tree 1 runs at ~45 % of the lanes).
+//   RING  : survivors (~16 % after two trees) are compacted (ballot + popc) into a per-warp ring in shared memory.
+//   TAIL  : when the ring holds more than kRing-32 entries (or the tile's window list is exhausted) the warp runs the generic
+//           lane-refill loop of the classic kernel, refilling from the ring, from tree head_trees on; with the ring empty and
+//           few lanes alive it parks the live (long-lived) windows back in the ring and returns to the head phase.
+// Results are identical to the classic kernel by construction (same leaves, same order of float32 adds, same threshold tests).
+// ring entry (kRingEntry = 12 bytes): pb (18 bits) | tree (6) | scale (8);  wid;  acc
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) scan_head_kernel(const TiledArgs A) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t wbar = smem_base + 16 + 8 * warp; // per-warp mbarrier: tile arrival
+  const uint32_t casc = kCascOff;
+  const uint32_t casc_bytes = (uint32_t)A.ks * kTreeRec;
+  const uint32_t casc_end = casc + casc_bytes;
+  const uint32_t my_tile = A.tiles_off + (uint32_t)warp * A.tile_bytes;
+  const uint32_t my_ring = A.ring_off + (uint32_t)warp * (kRing * kRingEntry);
+  const int HT = A.head_trees;
+
+  if (lane == 0 && warp < A.tile_warps) mbar_init(wbar, 1);
+  if (threadIdx.x < kLutSizes) smem[kLutOff + threadIdx.x] = 0xff;
+  stage_cascade(A, smem_base, casc, (casc_bytes + 15u) & ~15u);
+  if ((int)threadIdx.x < A.scan.nscales && threadIdx.x < 255) {
+    const int sz = A.scan.plan[threadIdx.x].s;
+    if (sz >= 0 && sz < kLutSizes) smem[kLutOff + sz] = (uint8_t)threadIdx.x;
+  }
+  // per-scale head tables: node (scale si, tree t, heap index idx) -> (o2 << 16) | (o1 & 0xffff), o = dr * pitch + dc with
+  // dr = (code_r * s) >> 8, dc = (code_c * s) >> 8 exactly as the generic walk computes them (core/pigo.go:126-127)
+  for (int q = threadIdx.x; q < A.head_nscales * HT * 64; q += blockDim.x) {
+    const int idx = q & 63, t = (q >> 6) % HT, si = q / (64 * HT);
+    int b = 0;
+    while (b + 1 < A.nbands && si >= A.band[b].scale_lo + A.band[b].nscales) ++b;
+    const int pitch = A.band[b].pitch, s = A.scan.plan[si].s;
+    const int cw = *reinterpret_cast<const int*>(smem + casc + t * kTreeRec + 4 * idx);
+    const int o1 = ((sx0(cw) * s) >> 8) * pitch + ((sx1(cw) * s) >> 8);
+    const int o2 = ((sx2(cw) * s) >> 8) * pitch + ((sx3(cw) * s) >> 8);
+    *reinterpret_cast<uint32_t*>(smem + A.head_off + 4 * q) = ((uint32_t)o2 << 16) | ((uint32_t)o1 & 0xffffu);
+  }
+  __syncthreads();
+
+  const ScanArgs& S = A.scan;
+  if (warp >= A.tile_warps) {
+    if (A.gather_ni >= 2) gather_role<2, 0>(A, smem, casc, casc_end);
+    else gather_role<1, 0>(A, smem, casc, casc_end);
+    return;
+  }
+  uint32_t tile_phase = 0;
+  const bool all_resident = A.ks >= S.tab.ntrees;
+  bool overflow_mode = false;
+  // generic-phase lane state
+  bool alive = false;
+  uint32_t pb = my_tile, tbo = casc, wid = 0;
+  int sv = 0;
+  float acc = 0.f;
+  // ring (warp-uniform)
+  int ring_head = 0, ring_cnt = 0;
+
+  for (;;) {
+    unsigned long long tg = 0;
+    if (lane == 0) tg = atomicAdd(S.chunk_counter, 1ull);
+    tg = __shfl_sync(FULL, tg, 0);
+    if (tg >= A.total_tiles) break;
+    const int frame = (int)(tg / A.tiles_per_frame);
+    wait_frames(S.ready, S.frame_base + (unsigned)frame + 1u);
+    int tf = (int)(tg % A.tiles_per_frame);
+    int b = 0;
+    while (b + 1 < A.nbands && tf >= A.band[b].ntiles) { tf -= A.band[b].ntiles; ++b; }
+    const TileBand B = A.band[b];
+    const int ty = tf / B.tiles_x, tx = tf - ty * B.tiles_x;
+    const int cx0 = B.org_x + tx * B.core, cy0 = ty * B.core;
+    const int gx0 = cx0 - B.halo_lo, gy0 = cy0 - B.halo_lo;
+    const int pitch = B.pitch;
+    const uint8_t* fb = S.frames + (size_t)frame * S.frame_stride;
+
+    int sc_i0 = 0, sc_j0 = 0, sc_nj = 0, sc_n = 0;
+    ScaleEntry e{};
+    if (lane < B.nscales) {
+      e = S.plan[B.scale_lo + lane];
+      const int i0 = ceil_div_pos(cy0 - e.off, e.step), i1 = min(e.nrows, ceil_div_pos(cy0 + B.core - e.off, e.step));
+      const int j0 = ceil_div_pos(cx0 - e.off, e.step), j1 = min(e.ncols, ceil_div_pos(cx0 + B.core - e.off, e.step));
+      sc_i0 = i0; sc_j0 = j0;
+      sc_nj = max(0, j1 - j0);
+      sc_n = max(0, i1 - i0) * sc_nj;
+    }
+    if (!__any_sync(FULL, sc_n > 0)) continue;
+
+    __syncwarp();
+    if (A.aligned) {
+      const int y_lo = max(gy0, 0), y_hi = min(gy0 + B.rows_t, S.rows);
+      const int x_lo = max(gx0, 0), x_hi = min(gx0 + pitch, S.dim);
+      const uint32_t row_bytes = (uint32_t)(x_hi - x_lo);
+      if (lane == 0) mbar_expect_tx(wbar, row_bytes * (uint32_t)(y_hi - y_lo));
+      __syncwarp();
+      for (int y = y_lo + lane; y < y_hi; y += 32)
+        tma_bulk_g2s(smem_base + my_tile + (uint32_t)((y - gy0) * pitch + (x_lo - gx0)), fb + (size_t)y * S.dim + x_lo, row_bytes, wbar);
+      mbar_wait(wbar, tile_phase);
+      tile_phase ^= 1u;
+    } else {
+      const int nbytes = B.rows_t * pitch;
+      for (int q = lane; q < nbytes; q += 32) {
+        const int row = q / pitch, xx = q - row * pitch;
+        const int y = gy0 + row, x = gx0 + xx;
+        if (y >= 0 && y < S.rows && x >= 0 && x < S.dim) smem[my_tile + q] = __ldg(fb + (size_t)y * S.dim + x);
+      }
+    }
+    __syncwarp();
+
+    // uniform cursor over the tile's window list (scale-major)
+    int cur_si = -1, cur_k = 0, cur_n = 0;
+    int u_s = 0, u_step = 0, u_nj = 1, u_ncols = 0, u_br = 0, u_bc = 0;
+    uint32_t u_wid0 = 0, u_magic = 0, u_hb = A.head_off;
+    bool exhausted = false;
+
+    for (;;) {
+      const bool any_alive = __any_sync(FULL, alive);
+      if (exhausted && ring_cnt == 0 && !any_alive) break;   // tile done
+      if (ring_cnt > kRing - 32 || (exhausted && (ring_cnt > 0 || any_alive))) {
+        // ================= TAIL: generic lane-refill loop fed by the ring =============================================
+        for (;;) {
+          const unsigned need = __ballot_sync(FULL, !alive);
+          const int take = min(__popc(need), ring_cnt);
+          if (take > 0) {
+            const int rank = __popc(need & lanemask_lt());
+            if (!alive && rank < take) {
+              int slot = ring_head + rank;
+              if (slot >= kRing) slot -= kRing;
+              const uint32_t* en = reinterpret_cast<const uint32_t*>(smem + my_ring + slot * kRingEntry);
+              const uint32_t w0 = en[0];
+              pb = w0 & 0x3ffffu; tbo = casc + ((w0 >> 18) & 0x3fu) * kTreeRec; sv = (int)(w0 >> 24);
+              wid = en[1]; acc = __uint_as_float(en[2]);
+              alive = true;
+            }
+            ring_head += take;
+            if (ring_head >= kRing) ring_head -= kRing;
+            ring_cnt -= take;
+            __syncwarp();
+          }
+          unsigned live = __ballot_sync(FULL, alive);
+          if (!live) break;
+          if (ring_cnt == 0 && !overflow_mode) {
+            if (!exhausted && __popc(live) < A.head_back) {
+              // park the long-lived windows in the ring (with their tree index) and go back to the head phase
+              int slot = ring_head + __popc(live & lanemask_lt());      // ring is empty: ring_head is also the write position
+              if (slot >= kRing) slot -= kRing;
+              if (alive) {
+                uint32_t* en = reinterpret_cast<uint32_t*>(smem + my_ring + slot * kRingEntry);
+                en[0] = pb | (((tbo - casc) / kTreeRec) << 18) | ((uint32_t)sv << 24);
+                en[1] = wid; en[2] = __float_as_uint(acc);
+                alive = false;
+              }
+              ring_cnt = __popc(live);
+              __syncwarp();
+              break;
+            }
+            if (exhausted && __popc(live) < A.tail_min) {
+              // tile drained: a thin group of stragglers goes to Q1 (finished one-per-lane by gather-v2)
+              unsigned qbase = 0;
+              if (lane == 0) qbase = atomicAdd(S.deep_count, (unsigned)__popc(live));
+              qbase = __shfl_sync(FULL, qbase, 0);
+              const unsigned pos = qbase + __popc(live & lanemask_lt());
+              const int qsi = scale_index_of(smem, sv);
+              if (alive && pos < S.deep_cap) {
+                S.deep[pos] = DeepItem{wid, pack_frame_si(frame, qsi), (int)((tbo - casc) / kTreeRec), acc};
+                alive = false;
+              }
+              live = __ballot_sync(FULL, alive);
+              if (!live) break;
+              overflow_mode = true;   // queue full: finish these items here
+            }
+          }
+          if (!alive) { tbo = casc; sv = 0; }   // dead lanes walk a harmless dummy (tree 0 at a valid pixel with s = 0)
+          if (!overflow_mode) {
+            int idx = 1, cw;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              cw = *reinterpret_cast<const int*>(smem + tbo + 4 * idx);
+              const int o1 = ((sx0(cw) * sv) >> 8) * pitch + ((sx1(cw) * sv) >> 8);
+              const int o2 = ((sx2(cw) * sv) >> 8) * pitch + ((sx3(cw) * sv) >> 8);
+              const uint32_t p1 = smem[pb + o1], p2 = smem[pb + o2];
+              idx = 2 * idx + (p1 <= p2 ? 1 : 0);                           // core/pigo.go:129-135
+            }
+            const float pred = *reinterpret_cast<const float*>(smem + tbo + 4 * idx);
+            const float thr = *reinterpret_cast<const float*>(smem + tbo + 512);
+            acc += pred;                                                   // core/pigo.go:137
+            alive = alive && !(acc <= thr);                                // :139-141
+            tbo += kTreeRec;
+            const bool at_end = alive && tbo == casc_end;
+            const unsigned mb = __ballot_sync(FULL, at_end);
+            if (mb) {
+              if (all_resident) {
+                if (at_end) {
+                  const float q = acc - thr;                               // :144
+                  if (q > 0.0f) {                                          // :246
+                    const int pos = atomicAdd(S.raw_count + frame, 1);
+                    if (pos < S.cap) S.raw[(size_t)frame * S.cap + pos] = RawDet{wid, q};
+                  }
+                  alive = false;
+                }
+              } else {
+                unsigned qbase = 0;
+                if (lane == 0) qbase = atomicAdd(S.long_count, (unsigned)__popc(mb));
+                qbase = __shfl_sync(FULL, qbase, 0);
+                const unsigned pos = qbase + __popc(mb & lanemask_lt());
+                const int qsi = scale_index_of(smem, sv);
+                bool failed = false;
+                if (at_end) {
+                  if (pos < S.long_cap) {
+                    S.longq[pos] = DeepItem{wid, pack_frame_si(frame, qsi), A.ks, acc};
+                    alive = false;
+                  } else {
+                    failed = true;
+                  }
+                }
+                if (__any_sync(FULL, failed)) overflow_mode = true;
+              }
+            }
+          } else {
+            // overflow mode (a queue was full, pathological): correct but slow; cascade rows beyond KS from global memory
+            const int tv = (int)((tbo - casc) / kTreeRec);
+            const bool res = tbo < casc_end;
+            int idx = 1;
+            for (int j = 0; j < 6; ++j) {
+              const int cw = res ? *reinterpret_cast<const int*>(smem + tbo + 4 * idx)
+                                 : __ldg(reinterpret_cast<const int*>(S.tab.codes + (size_t)tv * 256) + idx);
+              const int o1 = ((sx0(cw) * sv) >> 8) * pitch + ((sx1(cw) * sv) >> 8);
+              const int o2 = ((sx2(cw) * sv) >> 8) * pitch + ((sx3(cw) * sv) >> 8);
+              const uint32_t p1 = smem[pb + o1], p2 = smem[pb + o2];
+              idx = 2 * idx + (p1 <= p2 ? 1 : 0);
+            }
+            const float pred = res ? *reinterpret_cast<const float*>(smem + tbo + 4 * idx) : __ldg(S.tab.preds + (size_t)tv * 64 + idx - 64);
+            const float thr = res ? *reinterpret_cast<const float*>(smem + tbo + 512) : __ldg(S.tab.thresh + tv);
+            if (alive) {
+              acc += pred;
+              tbo += kTreeRec;
+              if (acc <= thr) {
+                alive = false;
+              } else if (tv + 1 == S.tab.ntrees) {
+                const float q = acc - thr;
+                if (q > 0.0f) {
+                  const int pos = atomicAdd(S.raw_count + frame, 1);
+                  if (pos < S.cap) S.raw[(size_t)frame * S.cap + pos] = RawDet{wid, q};
+                }
+                alive = false;
+              }
+            }
+          }
+        }
+        if (exhausted && ring_cnt == 0) break;     // tile done: ring empty, every lane dead
+        continue;
+      }
+
+      // ================= HEAD: 32 fresh windows of one scale, trees 0..HT-1 in lock-step ============================
+      if (cur_k == cur_n) {
+        int nsi = cur_si + 1;
+        int n = 0;
+        while (nsi < B.nscales && (n = __shfl_sync(FULL, sc_n, nsi)) == 0) ++nsi;
+        if (nsi >= B.nscales) { exhausted = true; continue; }
+        cur_si = nsi; cur_k = 0; cur_n = n;
+        u_s = __shfl_sync(FULL, e.s, nsi); u_step = __shfl_sync(FULL, e.step, nsi);
+        const int off = __shfl_sync(FULL, e.off, nsi), i0 = __shfl_sync(FULL, sc_i0, nsi), j0 = __shfl_sync(FULL, sc_j0, nsi);
+        u_nj = __shfl_sync(FULL, sc_nj, nsi); u_ncols = __shfl_sync(FULL, e.ncols, nsi);
+        u_br = off + i0 * u_step - gy0;
+        u_bc = off + j0 * u_step - gx0;
+        u_wid0 = __shfl_sync(FULL, e.wbase, nsi) + (uint32_t)i0 * (uint32_t)u_ncols + (uint32_t)j0;
+        u_magic = u_nj > 1 ? (uint32_t)((0x100000000ull + (unsigned)u_nj - 1) / (unsigned)u_nj) : 0u;
+        u_hb = A.head_off + (uint32_t)(B.scale_lo + nsi) * (uint32_t)(HT * 256);
+      }
+      {
+        const int n_take = min(32, cur_n - cur_k);
+        const uint32_t k = (uint32_t)(cur_k + min(lane, n_take - 1));      // surplus lanes repeat the last window (result ignored)
+        cur_k += n_take;
+        const uint32_t i = u_nj > 1 ? __umulhi(k, u_magic) : k;             // k / nj, exact for k*nj < 2^32
+        const uint32_t j = k - i * (uint32_t)u_nj;
+        const uint32_t hpb = my_tile + (uint32_t)((u_br + (int)i * u_step) * pitch + u_bc + (int)j * u_step);
+        float hacc = 0.f;
+        bool halive = lane < n_take;
+        for (int t = 0; t < HT; ++t) {
+          const uint32_t hb = u_hb + (uint32_t)t * 256u, rec = casc + (uint32_t)t * kTreeRec;
+          int idx = 1;
+#pragma unroll
+          for (int lv = 0; lv < 6; ++lv) {
+            const uint32_t nd = *reinterpret_cast<const uint32_t*>(smem + hb + 4 * idx);
+            const uint32_t p1 = smem[hpb + (int)(short)(nd & 0xffffu)], p2 = smem[hpb + ((int)nd >> 16)];
+            idx = 2 * idx + (p1 <= p2 ? 1 : 0);                             // core/pigo.go:129-135
+          }
+          hacc += *reinterpret_cast<const float*>(smem + rec + 4 * idx);   // :137 (float32, tree order)
+          halive = halive && !(hacc <= *reinterpret_cast<const float*>(smem + rec + 512));   // :139-141
+          if (!__any_sync(FULL, halive)) break;
+        }
+        const unsigned m = __ballot_sync(FULL, halive);
+        if (m) {
+          int slot = ring_head + ring_cnt + __popc(m & lanemask_lt());
+          if (slot >= kRing) slot -= kRing;
+          if (slot >= kRing) slot -= kRing;
+          if (halive) {
+            uint32_t* en = reinterpret_cast<uint32_t*>(smem + my_ring + slot * kRingEntry);
+            en[0] = hpb | ((uint32_t)HT << 18) | ((uint32_t)u_s << 24);
+            en[1] = u_wid0 + i * (uint32_t)u_ncols + j;
+            en[2] = __float_as_uint(hacc);
+          }
+          ring_cnt += __popc(m);
+          __syncwarp();
+        }
+      }
+    }
+  }
+}
+
 template <int NI, int MAXT>
 static void launch_tiled_ni(const TiledArgs& A, int grid, int threads, size_t smem, cudaStream_t st) {
   cudaFuncSetAttribute(scan_tiled_kernel<NI, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -699,6 +1018,11 @@ int gather2_ctas_per_sm(size_t smem, int ng, bool rot) {
 int tiled_max_threads(int ni) { return ni == 1 ? 1024 : (ni == 2 ? 768 : 512); }
 
 void launch_scan_tiled(const TiledArgs& A, int grid, int threads, size_t smem, int ni, cudaStream_t st) {
+  if (A.head_trees > 0) {
+    cudaFuncSetAttribute(scan_head_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    scan_head_kernel<1024><<<grid, threads, smem, st>>>(A);
+    return;
+  }
   switch (ni) {
     case 1: launch_tiled_ni<1, 1024>(A, grid, threads, smem, st); break;
     case 2: launch_tiled_ni<2, 768>(A, grid, threads, smem, st); break;

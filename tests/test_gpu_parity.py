@@ -262,13 +262,18 @@ VARIANTS = [
     {"scan_mode": 0, "gather_ks": 468, "tile_ks": 468, "tile_warps": 4, "gather_warps": 0},   # whole cascade resident: no Q2
     {"scan_mode": 0, "deep_flat": 1, "deep_group": 8, "tile_ks": 6},                          # flat deep loop, lots of Q2 traffic
     {"scan_mode": 3, "deep_flat": 1, "deep_group": 16, "gather_ks": 3},
+    {"scan_mode": 0, "tile_head": 2, "tile_warps": 22},                                       # dense head over trees 0..1, ring + generic tail
+    {"scan_mode": 0, "tile_head": 1, "tile_warps": 24, "head_back": 1},
+    {"scan_mode": 0, "tile_head": 3, "tile_warps": 6, "tile_ks": 5, "head_back": 16, "tile_tail_min": 33},   # everything spills, tiny prefix
+    {"scan_mode": 0, "tile_head": 4, "tile_warps": 12, "tile_ks": 63, "gather_warps": 0, "tile_tail_min": 0},
+    {"scan_mode": 0, "tile_head": 2, "tile_ks": 2},                                           # prefix not longer than the head: classic kernel
 ]
 
 
 @pytest.fixture
 def restore_options():
     keys = ["scan_mode", "tile_ni", "tile_warps", "tile_ks", "tile_tail_min", "tile_band_ratio", "tile_max_scale", "chunk",
-            "gather_warps", "gather_ks", "gather_ni", "sub_batch", "lanes", "deep_group", "gather_block", "fused_smem_kb", "tile_prefetch", "deep_flat"]
+            "gather_warps", "gather_ks", "gather_ni", "sub_batch", "lanes", "deep_group", "gather_block", "fused_smem_kb", "tile_prefetch", "deep_flat", "tile_head", "head_back"]
     saved = {k: pigo_b200.get_option(k) for k in keys}
     yield
     for k, v in saved.items():
