@@ -240,13 +240,22 @@ static int build_plan(int rows, int cols, int min_size, int max_size, double shi
 
 using namespace pigo;
 
-// Frames per pipeline group of one batch call: uniform groups, 128 frames by default (fewest kernel tails; the deferred
-// queues of a group stay bounded).  Host frames without in-kernel waiting (host_stream = 0): 64, because a whole group's
-// copy must finish before its scan starts and the first copy is exposed.
-static std::vector<int> group_schedule(int nframes, bool streamed) {
+// Frames per pipeline group of one batch call.  Resident frames: uniform groups of 128 (fewest kernel tails; the deferred
+// queues of a group stay bounded).  Host frames streamed behind the copy (host_stream): the groups TAPER -- 128, then half of
+// what is left, down to 32 -- because the step ends one group's tail kernels after the last chunk has arrived, and small
+// late groups cost nothing while the scan is waiting for the copy anyway.  Host frames without in-kernel waiting: 64.
+static std::vector<int> group_schedule(int nframes, bool resident, bool streamed) {
   std::vector<int> g;
   long long sub = g_opt.sub_batch.load();
-  if (sub <= 0) sub = streamed ? 128 : 64;
+  if (sub <= 0 && streamed && g_opt.stream_taper.load() != 0) {
+    for (int left = nframes; left > 0;) {
+      const int n = std::min(left, std::min(128, std::max(32, (left + 1) / 2)));
+      g.push_back(n);
+      left -= n;
+    }
+    return g;
+  }
+  if (sub <= 0) sub = (resident || streamed) ? 128 : 64;
   for (int left = nframes; left > 0; left -= (int)sub) g.push_back((int)std::min<long long>(sub, left));
   return g;
 }
@@ -325,7 +334,7 @@ static int scan_batch_on(pigo_cascade* c, int dev, const uint8_t* frames, int nf
   // kernels queued behind it start after every frame of the group has arrived (stream wait on the group's last chunk).
   const bool fused_path = rot_slot < 0 && c->depth == 6 && g_opt.scan_mode.load() == 0 && g_opt.tile_warps.load() > 0;
   const bool streamed = !frames_dev && g_opt.host_stream.load() != 0 && fused_path;
-  const std::vector<int> groups = group_schedule(nframes, frames_dev || streamed);
+  const std::vector<int> groups = group_schedule(nframes, frames_dev, streamed);
   const int nsub = (int)groups.size();
   int lanes = (int)std::min<long long>(std::max<long long>(1, g_opt.lanes.load()), kMaxLanes);
   if (nsub == 1 || rot_slot >= 0) lanes = 1;   // (the rotated node table is built once, on the first group's stream)

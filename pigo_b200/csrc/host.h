@@ -42,7 +42,9 @@ struct Options {
   std::atomic<long long> sub_batch{0};      // frames per pipeline group (0 = auto: 128 for resident frames; host frames: see host_first)
   std::atomic<long long> host_stream{1};    // host frames: 1 = the scan kernels start at once and wait IN-KERNEL for each frame's copy (a ready counter the copy
                                             // stream bumps after every chunk), so copy and scan overlap frame by frame; 0 = per-group copy events (round 1)
+  std::atomic<long long> stream_taper{1};   // host_stream: tapering group sizes (128, then half of the rest, >= 32) instead of uniform 128
   std::atomic<long long> copy_chunk{8};     // host_stream: frames per H2D copy chunk
+  std::atomic<long long> tile_core_cap{0};  // largest tile core edge in pixels; 0 = auto (16 for <= 2 frames, 32 for <= 8 frames: latency, else unlimited)
   std::atomic<long long> tile_head{0};      // fused kernel, tile role: 0 = classic lane refill from tree 0, N = dense head over the first N trees (scan_head_kernel)
   std::atomic<long long> head_back{12};     // dense head: generic phase parks its live windows and returns to the head below this many live lanes
   std::atomic<long long> deep_flat{0};      // deep kernel loop: 0 = groups of a warp fetch together (round 1), 1 = flat (fetch or step per iteration)
@@ -63,8 +65,8 @@ struct Options {
         {"tile_min_core_steps", &Options::tile_min_core_steps}, {"tile_prefetch", &Options::tile_prefetch},
          {"gather_block", &Options::gather_block}, {"deep_group", &Options::deep_group},
         {"sub_batch", &Options::sub_batch}, {"lanes", &Options::lanes}, {"tile_tail_min", &Options::tile_tail_min},
-        {"tile_band_ratio", &Options::tile_band_ratio}, {"timing", &Options::timing}, {"host_stream", &Options::host_stream}, {"copy_chunk", &Options::copy_chunk},
-        {"deep_flat", &Options::deep_flat}, {"tile_head", &Options::tile_head}, {"head_back", &Options::head_back}, {"rot_mode", &Options::rot_mode}, {"puploc_mode", &Options::puploc_mode}, {"puploc_stage", &Options::puploc_stage}};
+        {"tile_band_ratio", &Options::tile_band_ratio}, {"timing", &Options::timing}, {"host_stream", &Options::host_stream}, {"copy_chunk", &Options::copy_chunk}, {"stream_taper", &Options::stream_taper},
+        {"deep_flat", &Options::deep_flat}, {"tile_head", &Options::tile_head}, {"tile_core_cap", &Options::tile_core_cap}, {"head_back", &Options::head_back}, {"rot_mode", &Options::rot_mode}, {"puploc_mode", &Options::puploc_mode}, {"puploc_stage", &Options::puploc_stage}};
     for (const Entry& e : table)
       if (k == e.name) return &(this->*e.field);
     return nullptr;

@@ -43,7 +43,7 @@ struct TilePlan {
 };
 
 static TilePlan plan_bands(const std::vector<ScaleEntry>& plan, uint32_t tile_bytes, int max_scale, int ratio_pct, int min_core,
-                           int min_core_steps) {
+                           int min_core_steps, int core_cap = 512) {
   TilePlan tp;
   const int n = (int)plan.size();
   int a = 0;
@@ -57,7 +57,7 @@ static TilePlan plan_bands(const std::vector<ScaleEntry>& plan, uint32_t tile_by
       if (smax > max_scale || (long long)smax * 100 > (long long)s0 * ratio_pct) break;
       const int halo_lo = (smax + 1) / 2, halo_hi = (127 * smax) >> 8;
       int core = 0;
-      for (int c = 16; c <= 512; c += 16) {
+      for (int c = 16; c <= 512 && c <= std::max(16, core_cap); c += 16) {
         const int rows_t = halo_lo + c + halo_hi;
         const int pitch = (rows_t + 15) & ~15;
         if ((size_t)rows_t * pitch <= tile_bytes) core = c; else break;
@@ -123,7 +123,7 @@ struct FusedPlan {
   int W = 0, ks = 0, ni = 1;
   int head = 0;   // trees of the dense head (0 = classic tile role)
 };
-static FusedPlan plan_fused(const std::vector<ScaleEntry>& plan, int ntrees) {
+static FusedPlan plan_fused(const std::vector<ScaleEntry>& plan, int ntrees, int batch_frames = 1 << 20) {
   FusedPlan P;
   P.ni = (int)std::min<long long>(std::max<long long>(1, g_opt.tile_ni.load()), 4);
   const int max_warps = tiled_max_threads(P.ni) / 32;
@@ -136,12 +136,17 @@ static FusedPlan plan_fused(const std::vector<ScaleEntry>& plan, int ntrees) {
   // a resident prefix longer than the head and short enough for the 6-bit tree field of a ring entry
   P.head = (int)std::min<long long>(std::max<long long>(0, g_opt.tile_head.load()), kHeadTreesMax);
   if (P.ni != 1 || P.ks <= P.head || P.ks > 63 || g_opt.tile_prefetch.load()) P.head = 0;
+  // A tile is walked by ONE warp: with a frame or two in the batch, big tiles leave most warps idle and the call's latency is a
+  // tile's serial time (~60 us for a 48-pixel core).  Few frames -> small cores (more, shorter tiles).
+  long long core_cap = g_opt.tile_core_cap.load();
+  if (core_cap <= 0) core_cap = batch_frames <= 2 ? 16 : (batch_frames <= 8 ? 32 : 512);
   auto plan_with = [&](int head) {
     P.L = fused_layout(P.W, P.ks, (size_t)std::max<long long>(0, g_opt.fused_smem_kb.load()) * 1024, head);
     P.tp = TilePlan();
     if (P.L.ok)
       P.tp = plan_bands(plan, P.L.tile_bytes, max_scale, (int)std::max<long long>(100, g_opt.tile_band_ratio.load()),
-                        (int)std::max<long long>(16, g_opt.tile_min_core.load()), (int)std::max<long long>(1, g_opt.tile_min_core_steps.load()));
+                        (int)std::min<long long>(std::max<long long>(16, g_opt.tile_min_core.load()), core_cap),
+                        (int)std::max<long long>(1, core_cap < 512 ? 1 : g_opt.tile_min_core_steps.load()), (int)core_cap);
   };
   plan_with(P.head);
   if (P.head > 0) {
@@ -290,7 +295,7 @@ int run_scan(FaceReplica* c, Workspace* w, int lane, ScanArgs& A, unsigned long 
   int first_untiled = 0;
   bool blocks_done = false, tiled_ran = false;
   if (mode != 3 && !rot) {
-    FusedPlan P = plan_fused(w->plan_host, A.tab.ntrees);
+    FusedPlan P = plan_fused(w->plan_host, A.tab.ntrees, A.batch_frames);
     const TilePlan& tp = P.tp;
     const int W = P.W;
     int Wg = (int)std::min<long long>(std::max<long long>(0, g_opt.gather_warps.load()), tiled_max_threads(P.ni) / 32 - W);
