@@ -680,9 +680,9 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
 //           instructions instead of 21, there is no per-lane tree / scale state and no refill bookkeeping per walk.
 //           Lanes whose window was rejected idle until the batch ends (tree 1 runs at ~45 % of the lanes).
 //   RING  : survivors (~16 % after two trees) are compacted (ballot + popc) into a per-warp ring in shared memory.
-//   TAIL  : when the ring holds more than kRing-32 entries (or the tile's window list is exhausted) the warp runs the generic
-//           lane-refill loop of the classic kernel, refilling from the ring, from tree head_trees on; with the ring empty and
-//           few lanes alive it parks the live (long-lived) windows back in the ring and returns to the head phase.
+//   TAIL  : one iteration of the classic lane-refill walk (one tree per live lane, from tree head_trees on), its dead lanes
+//           re-armed from the ring.  Head batches run whenever the ring cannot re-arm all dead lanes, so the generic walk
+//           always runs with a (nearly) full warp; the live lanes keep their state in registers across head batches.
 // Results are identical to the classic kernel by construction (same leaves, same order of float32 adds, same threshold tests).
 // ring entry (kRingEntry = 12 bytes): pb (18 bits) | tree (6) | scale (8);  wid;  acc
 
@@ -795,160 +795,25 @@ __global__ void __launch_bounds__(MAXT, 1) scan_head_kernel(const TiledArgs A) {
     bool exhausted = false;
 
     for (;;) {
-      const bool any_alive = __any_sync(FULL, alive);
-      if (exhausted && ring_cnt == 0 && !any_alive) break;   // tile done
-      if (ring_cnt > kRing - 32 || (exhausted && (ring_cnt > 0 || any_alive))) {
-        // ================= TAIL: generic lane-refill loop fed by the ring =============================================
-        for (;;) {
-          const unsigned need = __ballot_sync(FULL, !alive);
-          const int take = min(__popc(need), ring_cnt);
-          if (take > 0) {
-            const int rank = __popc(need & lanemask_lt());
-            if (!alive && rank < take) {
-              int slot = ring_head + rank;
-              if (slot >= kRing) slot -= kRing;
-              const uint32_t* en = reinterpret_cast<const uint32_t*>(smem + my_ring + slot * kRingEntry);
-              const uint32_t w0 = en[0];
-              pb = w0 & 0x3ffffu; tbo = casc + ((w0 >> 18) & 0x3fu) * kTreeRec; sv = (int)(w0 >> 24);
-              wid = en[1]; acc = __uint_as_float(en[2]);
-              alive = true;
-            }
-            ring_head += take;
-            if (ring_head >= kRing) ring_head -= kRing;
-            ring_cnt -= take;
-            __syncwarp();
-          }
-          unsigned live = __ballot_sync(FULL, alive);
-          if (!live) break;
-          if (ring_cnt == 0 && !overflow_mode) {
-            if (!exhausted && __popc(live) < A.head_back) {
-              // park the long-lived windows in the ring (with their tree index) and go back to the head phase
-              int slot = ring_head + __popc(live & lanemask_lt());      // ring is empty: ring_head is also the write position
-              if (slot >= kRing) slot -= kRing;
-              if (alive) {
-                uint32_t* en = reinterpret_cast<uint32_t*>(smem + my_ring + slot * kRingEntry);
-                en[0] = pb | (((tbo - casc) / kTreeRec) << 18) | ((uint32_t)sv << 24);
-                en[1] = wid; en[2] = __float_as_uint(acc);
-                alive = false;
-              }
-              ring_cnt = __popc(live);
-              __syncwarp();
-              break;
-            }
-            if (exhausted && __popc(live) < A.tail_min) {
-              // tile drained: a thin group of stragglers goes to Q1 (finished one-per-lane by gather-v2)
-              unsigned qbase = 0;
-              if (lane == 0) qbase = atomicAdd(S.deep_count, (unsigned)__popc(live));
-              qbase = __shfl_sync(FULL, qbase, 0);
-              const unsigned pos = qbase + __popc(live & lanemask_lt());
-              const int qsi = scale_index_of(smem, sv);
-              if (alive && pos < S.deep_cap) {
-                S.deep[pos] = DeepItem{wid, pack_frame_si(frame, qsi), (int)((tbo - casc) / kTreeRec), acc};
-                alive = false;
-              }
-              live = __ballot_sync(FULL, alive);
-              if (!live) break;
-              overflow_mode = true;   // queue full: finish these items here
-            }
-          }
-          if (!alive) { tbo = casc; sv = 0; }   // dead lanes walk a harmless dummy (tree 0 at a valid pixel with s = 0)
-          if (!overflow_mode) {
-            int idx = 1, cw;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-              cw = *reinterpret_cast<const int*>(smem + tbo + 4 * idx);
-              const int o1 = ((sx0(cw) * sv) >> 8) * pitch + ((sx1(cw) * sv) >> 8);
-              const int o2 = ((sx2(cw) * sv) >> 8) * pitch + ((sx3(cw) * sv) >> 8);
-              const uint32_t p1 = smem[pb + o1], p2 = smem[pb + o2];
-              idx = 2 * idx + (p1 <= p2 ? 1 : 0);                           // core/pigo.go:129-135
-            }
-            const float pred = *reinterpret_cast<const float*>(smem + tbo + 4 * idx);
-            const float thr = *reinterpret_cast<const float*>(smem + tbo + 512);
-            acc += pred;                                                   // core/pigo.go:137
-            alive = alive && !(acc <= thr);                                // :139-141
-            tbo += kTreeRec;
-            const bool at_end = alive && tbo == casc_end;
-            const unsigned mb = __ballot_sync(FULL, at_end);
-            if (mb) {
-              if (all_resident) {
-                if (at_end) {
-                  const float q = acc - thr;                               // :144
-                  if (q > 0.0f) {                                          // :246
-                    const int pos = atomicAdd(S.raw_count + frame, 1);
-                    if (pos < S.cap) S.raw[(size_t)frame * S.cap + pos] = RawDet{wid, q};
-                  }
-                  alive = false;
-                }
-              } else {
-                unsigned qbase = 0;
-                if (lane == 0) qbase = atomicAdd(S.long_count, (unsigned)__popc(mb));
-                qbase = __shfl_sync(FULL, qbase, 0);
-                const unsigned pos = qbase + __popc(mb & lanemask_lt());
-                const int qsi = scale_index_of(smem, sv);
-                bool failed = false;
-                if (at_end) {
-                  if (pos < S.long_cap) {
-                    S.longq[pos] = DeepItem{wid, pack_frame_si(frame, qsi), A.ks, acc};
-                    alive = false;
-                  } else {
-                    failed = true;
-                  }
-                }
-                if (__any_sync(FULL, failed)) overflow_mode = true;
-              }
-            }
-          } else {
-            // overflow mode (a queue was full, pathological): correct but slow; cascade rows beyond KS from global memory
-            const int tv = (int)((tbo - casc) / kTreeRec);
-            const bool res = tbo < casc_end;
-            int idx = 1;
-            for (int j = 0; j < 6; ++j) {
-              const int cw = res ? *reinterpret_cast<const int*>(smem + tbo + 4 * idx)
-                                 : __ldg(reinterpret_cast<const int*>(S.tab.codes + (size_t)tv * 256) + idx);
-              const int o1 = ((sx0(cw) * sv) >> 8) * pitch + ((sx1(cw) * sv) >> 8);
-              const int o2 = ((sx2(cw) * sv) >> 8) * pitch + ((sx3(cw) * sv) >> 8);
-              const uint32_t p1 = smem[pb + o1], p2 = smem[pb + o2];
-              idx = 2 * idx + (p1 <= p2 ? 1 : 0);
-            }
-            const float pred = res ? *reinterpret_cast<const float*>(smem + tbo + 4 * idx) : __ldg(S.tab.preds + (size_t)tv * 64 + idx - 64);
-            const float thr = res ? *reinterpret_cast<const float*>(smem + tbo + 512) : __ldg(S.tab.thresh + tv);
-            if (alive) {
-              acc += pred;
-              tbo += kTreeRec;
-              if (acc <= thr) {
-                alive = false;
-              } else if (tv + 1 == S.tab.ntrees) {
-                const float q = acc - thr;
-                if (q > 0.0f) {
-                  const int pos = atomicAdd(S.raw_count + frame, 1);
-                  if (pos < S.cap) S.raw[(size_t)frame * S.cap + pos] = RawDet{wid, q};
-                }
-                alive = false;
-              }
-            }
-          }
+      // ================= HEAD: batches of 32 fresh windows of one scale, trees 0..HT-1 in lock-step ==================
+      // Run while the ring cannot re-arm the dead lanes of the generic phase (whose live lanes keep their state meanwhile).
+      unsigned need = __ballot_sync(FULL, !alive);
+      while (!exhausted && ring_cnt < __popc(need) && ring_cnt <= kRing - 32) {
+        if (cur_k == cur_n) {
+          int nsi = cur_si + 1;
+          int n = 0;
+          while (nsi < B.nscales && (n = __shfl_sync(FULL, sc_n, nsi)) == 0) ++nsi;
+          if (nsi >= B.nscales) { exhausted = true; break; }
+          cur_si = nsi; cur_k = 0; cur_n = n;
+          u_s = __shfl_sync(FULL, e.s, nsi); u_step = __shfl_sync(FULL, e.step, nsi);
+          const int off = __shfl_sync(FULL, e.off, nsi), i0 = __shfl_sync(FULL, sc_i0, nsi), j0 = __shfl_sync(FULL, sc_j0, nsi);
+          u_nj = __shfl_sync(FULL, sc_nj, nsi); u_ncols = __shfl_sync(FULL, e.ncols, nsi);
+          u_br = off + i0 * u_step - gy0;
+          u_bc = off + j0 * u_step - gx0;
+          u_wid0 = __shfl_sync(FULL, e.wbase, nsi) + (uint32_t)i0 * (uint32_t)u_ncols + (uint32_t)j0;
+          u_magic = u_nj > 1 ? (uint32_t)((0x100000000ull + (unsigned)u_nj - 1) / (unsigned)u_nj) : 0u;
+          u_hb = A.head_off + (uint32_t)(B.scale_lo + nsi) * (uint32_t)(HT * 256);
         }
-        if (exhausted && ring_cnt == 0) break;     // tile done: ring empty, every lane dead
-        continue;
-      }
-
-      // ================= HEAD: 32 fresh windows of one scale, trees 0..HT-1 in lock-step ============================
-      if (cur_k == cur_n) {
-        int nsi = cur_si + 1;
-        int n = 0;
-        while (nsi < B.nscales && (n = __shfl_sync(FULL, sc_n, nsi)) == 0) ++nsi;
-        if (nsi >= B.nscales) { exhausted = true; continue; }
-        cur_si = nsi; cur_k = 0; cur_n = n;
-        u_s = __shfl_sync(FULL, e.s, nsi); u_step = __shfl_sync(FULL, e.step, nsi);
-        const int off = __shfl_sync(FULL, e.off, nsi), i0 = __shfl_sync(FULL, sc_i0, nsi), j0 = __shfl_sync(FULL, sc_j0, nsi);
-        u_nj = __shfl_sync(FULL, sc_nj, nsi); u_ncols = __shfl_sync(FULL, e.ncols, nsi);
-        u_br = off + i0 * u_step - gy0;
-        u_bc = off + j0 * u_step - gx0;
-        u_wid0 = __shfl_sync(FULL, e.wbase, nsi) + (uint32_t)i0 * (uint32_t)u_ncols + (uint32_t)j0;
-        u_magic = u_nj > 1 ? (uint32_t)((0x100000000ull + (unsigned)u_nj - 1) / (unsigned)u_nj) : 0u;
-        u_hb = A.head_off + (uint32_t)(B.scale_lo + nsi) * (uint32_t)(HT * 256);
-      }
-      {
         const int n_take = min(32, cur_n - cur_k);
         const uint32_t k = (uint32_t)(cur_k + min(lane, n_take - 1));      // surplus lanes repeat the last window (result ignored)
         cur_k += n_take;
@@ -983,6 +848,123 @@ __global__ void __launch_bounds__(MAXT, 1) scan_head_kernel(const TiledArgs A) {
           }
           ring_cnt += __popc(m);
           __syncwarp();
+        }
+      }
+
+      // ================= TAIL: generic lane-refill walk, re-armed from the ring =======================================
+      {
+        const int take = min(__popc(need), ring_cnt);
+        if (take > 0) {
+          const int rank = __popc(need & lanemask_lt());
+          if (!alive && rank < take) {
+            int slot = ring_head + rank;
+            if (slot >= kRing) slot -= kRing;
+            const uint32_t* en = reinterpret_cast<const uint32_t*>(smem + my_ring + slot * kRingEntry);
+            const uint32_t w0 = en[0];
+            pb = w0 & 0x3ffffu; tbo = casc + ((w0 >> 18) & 0x3fu) * kTreeRec; sv = (int)(w0 >> 24);
+            wid = en[1]; acc = __uint_as_float(en[2]);
+            alive = true;
+          }
+          ring_head += take;
+          if (ring_head >= kRing) ring_head -= kRing;
+          ring_cnt -= take;
+          __syncwarp();
+        }
+      }
+      unsigned live = __ballot_sync(FULL, alive);
+      if (!live) {
+        if (exhausted && ring_cnt == 0) break;       // tile done
+        continue;
+      }
+      if (exhausted && ring_cnt == 0 && !overflow_mode && __popc(live) < A.tail_min) {
+        // tile drained: a thin group of stragglers goes to Q1 (finished one-per-lane by gather-v2)
+        unsigned qbase = 0;
+        if (lane == 0) qbase = atomicAdd(S.deep_count, (unsigned)__popc(live));
+        qbase = __shfl_sync(FULL, qbase, 0);
+        const unsigned pos = qbase + __popc(live & lanemask_lt());
+        const int qsi = scale_index_of(smem, sv);
+        if (alive && pos < S.deep_cap) {
+          S.deep[pos] = DeepItem{wid, pack_frame_si(frame, qsi), (int)((tbo - casc) / kTreeRec), acc};
+          alive = false;
+        }
+        live = __ballot_sync(FULL, alive);
+        if (!live) break;
+        overflow_mode = true;   // queue full: finish these items here
+      }
+      if (!alive) { tbo = casc; sv = 0; }   // dead lanes walk a harmless dummy (tree 0 at a valid pixel with s = 0)
+      if (!overflow_mode) {
+        int idx = 1, cw;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          cw = *reinterpret_cast<const int*>(smem + tbo + 4 * idx);
+          const int o1 = ((sx0(cw) * sv) >> 8) * pitch + ((sx1(cw) * sv) >> 8);
+          const int o2 = ((sx2(cw) * sv) >> 8) * pitch + ((sx3(cw) * sv) >> 8);
+          const uint32_t p1 = smem[pb + o1], p2 = smem[pb + o2];
+          idx = 2 * idx + (p1 <= p2 ? 1 : 0);                           // core/pigo.go:129-135
+        }
+        const float pred = *reinterpret_cast<const float*>(smem + tbo + 4 * idx);
+        const float thr = *reinterpret_cast<const float*>(smem + tbo + 512);
+        acc += pred;                                                   // core/pigo.go:137
+        alive = alive && !(acc <= thr);                                // :139-141
+        tbo += kTreeRec;
+        const bool at_end = alive && tbo == casc_end;
+        const unsigned mb = __ballot_sync(FULL, at_end);
+        if (mb) {
+          if (all_resident) {
+            if (at_end) {
+              const float q = acc - thr;                               // :144
+              if (q > 0.0f) {                                          // :246
+                const int pos = atomicAdd(S.raw_count + frame, 1);
+                if (pos < S.cap) S.raw[(size_t)frame * S.cap + pos] = RawDet{wid, q};
+              }
+              alive = false;
+            }
+          } else {
+            unsigned qbase = 0;
+            if (lane == 0) qbase = atomicAdd(S.long_count, (unsigned)__popc(mb));
+            qbase = __shfl_sync(FULL, qbase, 0);
+            const unsigned pos = qbase + __popc(mb & lanemask_lt());
+            const int qsi = scale_index_of(smem, sv);
+            bool failed = false;
+            if (at_end) {
+              if (pos < S.long_cap) {
+                S.longq[pos] = DeepItem{wid, pack_frame_si(frame, qsi), A.ks, acc};
+                alive = false;
+              } else {
+                failed = true;
+              }
+            }
+            if (__any_sync(FULL, failed)) overflow_mode = true;
+          }
+        }
+      } else {
+        // overflow mode (a queue was full, pathological): correct but slow; cascade rows beyond KS from global memory
+        const int tv = (int)((tbo - casc) / kTreeRec);
+        const bool res = tbo < casc_end;
+        int idx = 1;
+        for (int j = 0; j < 6; ++j) {
+          const int cw = res ? *reinterpret_cast<const int*>(smem + tbo + 4 * idx)
+                             : __ldg(reinterpret_cast<const int*>(S.tab.codes + (size_t)tv * 256) + idx);
+          const int o1 = ((sx0(cw) * sv) >> 8) * pitch + ((sx1(cw) * sv) >> 8);
+          const int o2 = ((sx2(cw) * sv) >> 8) * pitch + ((sx3(cw) * sv) >> 8);
+          const uint32_t p1 = smem[pb + o1], p2 = smem[pb + o2];
+          idx = 2 * idx + (p1 <= p2 ? 1 : 0);
+        }
+        const float pred = res ? *reinterpret_cast<const float*>(smem + tbo + 4 * idx) : __ldg(S.tab.preds + (size_t)tv * 64 + idx - 64);
+        const float thr = res ? *reinterpret_cast<const float*>(smem + tbo + 512) : __ldg(S.tab.thresh + tv);
+        if (alive) {
+          acc += pred;
+          tbo += kTreeRec;
+          if (acc <= thr) {
+            alive = false;
+          } else if (tv + 1 == S.tab.ntrees) {
+            const float q = acc - thr;
+            if (q > 0.0f) {
+              const int pos = atomicAdd(S.raw_count + frame, 1);
+              if (pos < S.cap) S.raw[(size_t)frame * S.cap + pos] = RawDet{wid, q};
+            }
+            alive = false;
+          }
         }
       }
     }
