@@ -281,6 +281,14 @@ def main():
         if n > 0:
             kt[name] = {"launches": int(n), "avg_us": ns / n / 1e3, "total_ms": ns / 1e6}
     pigo_b200.set_option("timing", 0)
+    # useful-lane metric of the tile role: live lanes per walk iteration (dead lanes walk a dummy tree), one extra step
+    pigo_b200.set_option("walk_stats", 1)
+    step_device()
+    torch.cuda.synchronize()
+    wu, wi = pigo_b200.get_option("walk_useful"), pigo_b200.get_option("walk_iters")
+    pigo_b200.set_option("walk_stats", 0)
+    lanes = {"live_lanes_per_tile_walk_iteration": (wu / wi) if wi > 0 else None, "tile_role_tree_walks_per_step": int(wu),
+             "tile_role_walk_iterations_per_step": int(wi)}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -316,7 +324,7 @@ def main():
                     "traffic": traffic, "kernel": dom[0], "kernel_launch_ms": launch_ms, "frames_per_launch": frames_per_launch,
                     "scan_kernels_ms_per_step": scan_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                     "traffic_note": traffic_src,
-                    "kernels": kt, "note": "path is issue/latency/L2-transaction bound (2.3 algorithmic B/window), not HBM "
+                    "kernels": kt, "tile_role_lanes": lanes, "note": "path is issue/latency/L2-transaction bound (2.3 algorithmic B/window), not HBM "
                     "bound; see DESIGN.md"}
 
     # ---- end to end through the host API: pinned H2D of the frames + D2H of counts and detections every step

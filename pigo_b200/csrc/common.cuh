@@ -160,6 +160,8 @@ struct TiledArgs {
   int32_t head_trees;                     // 0 = classic kernel
   int32_t head_nscales;                   // ladder entries [0, head_nscales) are tiled
   uint32_t head_off, ring_off, tiles_off;
+  int32_t gather_limit;                   // gather role: trees a window walks here before it is handed to the deep kernel (<= ks)
+  unsigned long long* stats;              // developer counter (option walk_stats): [0] += live lanes, [1] += 1 per tile-role walk iteration
   int32_t head_back;                      // generic phase: with an empty ring and fewer live lanes than this, park them in the ring and go back to the head
 };
 

@@ -18,6 +18,9 @@ extern std::atomic<long long> g_launches;
 // event pair on its stream; "t_<name>_ns" / "t_<name>_n" return the summed device time and the launch count.
 enum TimeSlot { T_TILED = 0, T_GATHER, T_DEEP, T_FINALIZE, T_CLUSTER, T_PUPLOC, T_GRAY, T_SEEDS, T_ROTTAB, T_YCBCR, T_NSLOTS };
 void timing_reset();
+void walk_stats_reset();
+long long walk_stats_query(int which);
+unsigned long long* walk_stats_buffer(int dev);   // nullptr unless option walk_stats is on
 long long timing_query(const std::string& key);
 void timing_begin(int slot, cudaStream_t st);
 void timing_end(int slot, cudaStream_t st);
@@ -44,7 +47,9 @@ struct Options {
                                             // stream bumps after every chunk), so copy and scan overlap frame by frame; 0 = per-group copy events (round 1)
   std::atomic<long long> stream_taper{1};   // host_stream: tapering group sizes (128, then half of the rest, >= 32) instead of uniform 128
   std::atomic<long long> copy_chunk{8};     // host_stream: frames per H2D copy chunk
-  std::atomic<long long> tile_core_cap{0};  // largest tile core edge in pixels; 0 = auto (16 for <= 2 frames, 32 for <= 8 frames: latency, else unlimited)
+  std::atomic<long long> walk_stats{0};     // 1 = count live lanes per walk iteration of the tile role ("walk_useful" / "walk_iters" read them back)
+  std::atomic<long long> tile_core_cap{0};  // largest tile core edge in pixels; 0 = unlimited
+  std::atomic<long long> gather_limit{0};   // trees a gather-role window walks before it goes to the deep kernel; 0 = auto (8 for <= 4 frames: latency, else all resident)
   std::atomic<long long> tile_head{0};      // fused kernel, tile role: 0 = classic lane refill from tree 0, N = dense head over the first N trees (scan_head_kernel)
   std::atomic<long long> head_back{12};     // dense head: generic phase parks its live windows and returns to the head below this many live lanes
   std::atomic<long long> deep_flat{0};      // deep kernel loop: 0 = groups of a warp fetch together (round 1), 1 = flat (fetch or step per iteration)
@@ -66,7 +71,7 @@ struct Options {
          {"gather_block", &Options::gather_block}, {"deep_group", &Options::deep_group},
         {"sub_batch", &Options::sub_batch}, {"lanes", &Options::lanes}, {"tile_tail_min", &Options::tile_tail_min},
         {"tile_band_ratio", &Options::tile_band_ratio}, {"timing", &Options::timing}, {"host_stream", &Options::host_stream}, {"copy_chunk", &Options::copy_chunk}, {"stream_taper", &Options::stream_taper},
-        {"deep_flat", &Options::deep_flat}, {"tile_head", &Options::tile_head}, {"tile_core_cap", &Options::tile_core_cap}, {"head_back", &Options::head_back}, {"rot_mode", &Options::rot_mode}, {"puploc_mode", &Options::puploc_mode}, {"puploc_stage", &Options::puploc_stage}};
+        {"deep_flat", &Options::deep_flat}, {"tile_head", &Options::tile_head}, {"tile_core_cap", &Options::tile_core_cap}, {"walk_stats", &Options::walk_stats}, {"gather_limit", &Options::gather_limit}, {"head_back", &Options::head_back}, {"rot_mode", &Options::rot_mode}, {"puploc_mode", &Options::puploc_mode}, {"puploc_stage", &Options::puploc_stage}};
     for (const Entry& e : table)
       if (k == e.name) return &(this->*e.field);
     return nullptr;
@@ -76,10 +81,13 @@ struct Options {
     if (!f) return false;
     *f = v;
     if (f == &timing) timing_reset();
+    if (f == &walk_stats) walk_stats_reset();
     return true;
   }
   long long get(const std::string& k) {
     if (k.rfind("t_", 0) == 0) return timing_query(k);
+    if (k == "walk_useful") return walk_stats_query(0);
+    if (k == "walk_iters") return walk_stats_query(1);
     std::atomic<long long>* f = find(k);
     return f ? f->load() : -1;
   }

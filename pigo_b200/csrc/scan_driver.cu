@@ -136,10 +136,9 @@ static FusedPlan plan_fused(const std::vector<ScaleEntry>& plan, int ntrees, int
   // a resident prefix longer than the head and short enough for the 6-bit tree field of a ring entry
   P.head = (int)std::min<long long>(std::max<long long>(0, g_opt.tile_head.load()), kHeadTreesMax);
   if (P.ni != 1 || P.ks <= P.head || P.ks > 63 || g_opt.tile_prefetch.load()) P.head = 0;
-  // A tile is walked by ONE warp: with a frame or two in the batch, big tiles leave most warps idle and the call's latency is a
-  // tile's serial time (~60 us for a 48-pixel core).  Few frames -> small cores (more, shorter tiles).
+  // Optional cap on the tile core (developer knob; more, shorter tiles).
   long long core_cap = g_opt.tile_core_cap.load();
-  if (core_cap <= 0) core_cap = batch_frames <= 2 ? 16 : (batch_frames <= 8 ? 32 : 512);
+  if (core_cap <= 0) core_cap = 512;   // (measured: 16/32-pixel cores for a single frame are SLOWER, 0.26 vs 0.22 ms: tile fills dominate)
   auto plan_with = [&](int head) {
     P.L = fused_layout(P.W, P.ks, (size_t)std::max<long long>(0, g_opt.fused_smem_kb.load()) * 1024, head);
     P.tp = TilePlan();
@@ -214,6 +213,39 @@ int describe_plan(const std::vector<ScaleEntry>& plan, uint64_t wins, int ntrees
   return PIGO_OK;
 }
 
+// ---- developer counter: live lanes per walk iteration of the tile role (option walk_stats) ----------------------------------
+static unsigned long long* g_walk_stats[kMaxDevices] = {};
+unsigned long long* walk_stats_buffer(int dev) {
+  if (!g_opt.walk_stats.load() || dev < 0 || dev >= kMaxDevices) return nullptr;
+  if (!g_walk_stats[dev]) {
+    if (cudaMalloc((void**)&g_walk_stats[dev], 16) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    cudaMemset(g_walk_stats[dev], 0, 16);
+  }
+  return g_walk_stats[dev];
+}
+void walk_stats_reset() {
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < kMaxDevices; ++d)
+    if (g_walk_stats[d]) { cudaSetDevice(d); cudaMemset(g_walk_stats[d], 0, 16); }
+  cudaSetDevice(cur);
+}
+long long walk_stats_query(int which) {
+  long long total = 0;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < kMaxDevices; ++d)
+    if (g_walk_stats[d]) {
+      unsigned long long v[2] = {0, 0};
+      cudaSetDevice(d);
+      cudaDeviceSynchronize();
+      cudaMemcpy(v, g_walk_stats[d], 16, cudaMemcpyDeviceToHost);
+      total += (long long)v[which & 1];
+    }
+  cudaSetDevice(cur);
+  return total;
+}
+
 static int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_err(PIGO_E_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
@@ -283,6 +315,10 @@ int run_scan(FaceReplica* c, Workspace* w, int lane, ScanArgs& A, unsigned long 
   T.gather_blocks_per_frame = 0;
   T.tile_prefetch = g_opt.tile_prefetch.load() ? 1 : 0;
   T.gather_ni = (int)std::min<long long>(std::max<long long>(1, g_opt.gather_ni.load()), 3);
+  // latency mode (a frame or two): gather-role windows leave for the deep kernel after a few trees
+  long long glimit = g_opt.gather_limit.load();
+  if (glimit <= 0) glimit = A.batch_frames <= 4 ? 8 : (1 << 20);
+  T.gather_limit = (int)std::min<long long>(glimit, 1 << 20);
   // small batches (a frame or two) cannot fill the GPU with 256-window blocks: use 64-window blocks then
   // (decided from the frames of the whole API call, not of this pipeline group: the block prefix lives in the shared plan)
   T.gb_shift = (g_opt.gather_block.load() == 8 || (g_opt.gather_block.load() == 0 && A.batch_frames <= 4)) ? 3 : 4;
@@ -308,6 +344,7 @@ int run_scan(FaceReplica* c, Workspace* w, int lane, ScanArgs& A, unsigned long 
       F.total_tiles = (unsigned long long)tp.tiles_per_frame * A.nframes;
       F.tile_warps = W;
       F.consume_q1 = 0;
+      F.stats = walk_stats_buffer(c->device);
       F.head_trees = P.head; F.head_nscales = tp.first_untiled;
       F.head_off = (uint32_t)P.L.head_off; F.ring_off = (uint32_t)P.L.ring_off; F.tiles_off = (uint32_t)P.L.tiles_off;
       F.head_back = (int)std::min<long long>(std::max<long long>(1, g_opt.head_back.load()), kRing - 32);
@@ -342,7 +379,7 @@ int run_scan(FaceReplica* c, Workspace* w, int lane, ScanArgs& A, unsigned long 
   {
     TiledArgs G = T;
     G.scan.ready = nullptr;
-    G.ks = round_ks(g_opt.gather_ks.load());
+    G.ks = round_ks(std::min<long long>(g_opt.gather_ks.load(), T.gather_limit));
     G.consume_q1 = tiled_ran ? 1 : 0;
     G.tile_warps = 0;
     if (!blocks_done && first_untiled < A.nscales) {

@@ -368,8 +368,11 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
 
   const ScanArgs& S = A.scan;
   if (warp >= A.tile_warps) {   // warp-specialised: the remaining warps scan the large scales by global-memory gathers
-    if (A.gather_ni >= 2) gather_role<2, 0>(A, smem, casc, casc_end);
-    else gather_role<1, 0>(A, smem, casc, casc_end);
+    // (a gather-role walk is a chain of L2 round trips, ~4000 cycles per tree: with a frame or two in the batch the host lowers
+    // gather_limit so that long-lived windows move early to the deep kernel, which walks 32 trees per step)
+    const uint32_t g_end = casc + (uint32_t)min(A.ks, max(1, A.gather_limit)) * kTreeRec;
+    if (A.gather_ni >= 2) gather_role<2, 0>(A, smem, casc, g_end);
+    else gather_role<1, 0>(A, smem, casc, g_end);
     return;
   }
   uint32_t tile_phase = 0;
@@ -529,6 +532,12 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
         }
       }
 
+      if (A.stats != nullptr) {   // developer counter: useful (live) lanes per walk iteration of the tile role
+        unsigned nlive = 0;
+#pragma unroll
+        for (int u = 0; u < NI; ++u) nlive += __popc(__ballot_sync(FULL, alive[u]));
+        if (lane == 0) { atomicAdd(A.stats, (unsigned long long)nlive); atomicAdd(A.stats + 1, (unsigned long long)NI); }
+      }
       // ================= one tree per live item =================================================================
       if (!overflow_mode) {
         int idx[NI], cw[NI];
