@@ -370,6 +370,40 @@ def main():
         med = float(np.mean(list(lat.values())))
         single = {"workload": "configs[1]: one 1920x1080 frame, device resident", "ms_per_frame_by_class": lat,
                   "windows_per_s": W / (med * 1e-3)}
+        # the same call captured once into a CUDA graph and replayed (launch overhead off the critical path)
+        try:
+            glat = {}
+            for label, idx in (("U", 0), ("S", 1), ("F", 2)):
+                fr = d_frames[idx:idx + 1]
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream, capture_error_mode="relaxed"):
+                    clf.run_cascade_batch_device(fr.data_ptr(), 1, ROWS * COLS, ROWS, COLS, COLS, *PARAMS, 0.0,
+                                                 one_out.data_ptr(), cap, one_cnt.data_ptr(), stream.cuda_stream)
+                ts = []
+                for it in range(13):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(stream)
+                    g.replay()
+                    b.record(stream)
+                    torch.cuda.synchronize()
+                    if it >= 3:
+                        ts.append(a.elapsed_time(b))
+                glat[label] = float(np.median(ts))
+            single["cuda_graph_ms_per_frame_by_class"] = glat
+        except Exception as e:   # noqa: BLE001 -- the graph leg is informative, never fatal
+            single["cuda_graph_error"] = repr(e)[:200]
+        # host API: pigo_run_cascade on one host frame (H2D, scan, D2H, sync), wall clock
+        hts = []
+        one_h = np.zeros(cap, dtype=pigo_b200.DET_DTYPE)
+        n_h = C.c_int()
+        for it in range(23):
+            t0 = time.perf_counter()
+            rc = L.pigo_run_cascade(clf._h, pinned[2].data_ptr(), ROWS, COLS, COLS, PARAMS[0], PARAMS[1], PARAMS[2], PARAMS[3], 0.0,
+                                    one_h.ctypes.data, cap, C.byref(n_h))
+            if it >= 3:
+                hts.append((time.perf_counter() - t0) * 1e3)
+            assert rc == 0
+        single["host_api_ms_per_frame"] = float(np.median(hts))
 
     # ---- configs[3]: 3840x2160 frames, rotated scan at EVERY table slot a = k/32 (rank 0, N=1 only: a sweep, not a scaling case)
     config4 = None

@@ -75,13 +75,26 @@ long long timing_query(const std::string& key) {
 
 // A workspace can be handed to another caller (another thread / stream) while the asynchronous work of its previous
 // user is still running on that user's stream: order every new user behind the last recorded use.
+static bool stream_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs == cudaStreamCaptureStatusActive;
+}
+
 static int ws_enter(Workspace* w, cudaStream_t st) {
   if (!w->busy && cudaEventCreateWithFlags(&w->busy, cudaEventDisableTiming) != cudaSuccess) return set_err(PIGO_E_CUDA, "event creation failed");
+  if (stream_capturing(st)) {   // CUDA-graph capture of a device-output call: no events cross the capture boundary (see scan_batch_on)
+    if (w->busy_valid) cudaEventSynchronize(w->busy);
+    w->busy_valid = false;
+    w->active_stream_set = false;
+    return PIGO_OK;
+  }
   if (w->busy_valid && cudaStreamWaitEvent(st, w->busy, 0) != cudaSuccess) return set_err(PIGO_E_CUDA, "cudaStreamWaitEvent failed");
   w->active_stream = st; w->active_stream_set = true;   // WsGuard records `busy` on it when the call ends, however it ends
   return PIGO_OK;
 }
 static int ws_leave_async(Workspace* w, cudaStream_t st) {
+  if (stream_capturing(st)) { w->active_stream_set = false; return PIGO_OK; }
   if (cudaEventRecord(w->busy, st) != cudaSuccess) return set_err(PIGO_E_CUDA, "cudaEventRecord failed");
   w->busy_valid = true;
   w->active_stream_set = false;
@@ -241,18 +254,33 @@ static int build_plan(int rows, int cols, int min_size, int max_size, double shi
 using namespace pigo;
 
 // Frames per pipeline group of one batch call.  Resident frames: uniform groups of 128 (fewest kernel tails; the deferred
-// queues of a group stay bounded).  Host frames streamed behind the copy (host_stream): the groups TAPER -- 128, then half of
-// what is left, down to 32 -- because the step ends one group's tail kernels after the last chunk has arrived, and small
-// late groups cost nothing while the scan is waiting for the copy anyway.  Host frames without in-kernel waiting: 64.
+// queues of a group stay bounded).  Host frames without in-kernel waiting: 64.  Host frames streamed behind the copy
+// (host_stream): uniform 128 by default.  PCIe (50.7 GB/s measured: 10.5 ms for 256 x 1080p) and the scan (10.4 ms) run at
+// the same rate, so a step costs about  [time the scan idles behind the first copy chunks] + [scan]  and also at least
+// [copy] + [tail kernels of the last group]; stream_taper = 1 (128, then half of the rest) shortens the second term but
+// its small groups lengthen the first (measured 13.2 vs 12.6 ms); stream_taper = 2 (1/8, 1/4, 3/8, 3/16, 1/16 of the batch)
+// tries to shorten both.
 static std::vector<int> group_schedule(int nframes, bool resident, bool streamed) {
   std::vector<int> g;
   long long sub = g_opt.sub_batch.load();
-  if (sub <= 0 && streamed && g_opt.stream_taper.load() != 0) {
+  const long long taper = g_opt.stream_taper.load();
+  if (sub <= 0 && streamed && taper == 1) {
     for (int left = nframes; left > 0;) {
       const int n = std::min(left, std::min(128, std::max(32, (left + 1) / 2)));
       g.push_back(n);
       left -= n;
     }
+    return g;
+  }
+  if (sub <= 0 && streamed && taper == 2 && nframes >= 64) {
+    static const int sixteenths[5] = {2, 4, 6, 3, 1};
+    int left = nframes;
+    for (int k = 0; k < 5 && left > 0; ++k) {
+      const int n = k == 4 ? left : std::min(left, std::min(128, std::max(8, nframes * sixteenths[k] / 16)));
+      g.push_back(n);
+      left -= n;
+    }
+    if (left > 0) g.push_back(left);
     return g;
   }
   if (sub <= 0) sub = (resident || streamed) ? 128 : 64;
@@ -277,6 +305,17 @@ static int scan_batch_on(pigo_cascade* c, int dev, const uint8_t* frames, int nf
   if (!w) return set_err(PIGO_E_CUDA, "could not create a CUDA stream");
   cudaStream_t st = stream_ ? (cudaStream_t)stream_ : w->stream;
   if ((rc = ws_enter(w, st))) return rc;
+  // CUDA-graph capture (device frames + device outputs on the caller's capturing stream, after one un-captured warm-up call
+  // with the same arguments): the captured kernels keep using this workspace's scratch on every replay, so the workspace
+  // is taken out of the pool for good -- it belongs to the graph from now on.
+  const bool capturing = stream_capturing(st);
+  if (capturing) {
+    if (!(flags & PIGO_FRAMES_DEVICE) || !(flags & PIGO_OUT_DEVICE)) return set_err(PIGO_E_INVALID, "stream capture needs device frames and device outputs");
+    if (w->p_rows != rows || w->p_cols != cols || w->p_min != min_size || w->p_max != max_size || w->p_shift != shift_factor ||
+        w->p_scale != scale_factor)
+      return set_err(PIGO_E_INVALID, "stream capture: run the same call once outside the capture first (the plan upload synchronises)");
+    g.w = nullptr;
+  }
 
   // plan (cached per workspace)
   if (w->p_rows != rows || w->p_cols != cols || w->p_min != min_size || w->p_max != max_size || w->p_shift != shift_factor ||

@@ -45,7 +45,7 @@ struct Options {
   std::atomic<long long> sub_batch{0};      // frames per pipeline group (0 = auto: 128 for resident frames; host frames: see host_first)
   std::atomic<long long> host_stream{1};    // host frames: 1 = the scan kernels start at once and wait IN-KERNEL for each frame's copy (a ready counter the copy
                                             // stream bumps after every chunk), so copy and scan overlap frame by frame; 0 = per-group copy events (round 1)
-  std::atomic<long long> stream_taper{1};   // host_stream: tapering group sizes (128, then half of the rest, >= 32) instead of uniform 128
+  std::atomic<long long> stream_taper{0};   // host_stream group sizes: 0 = uniform 128, 1 = 128 then half of the rest (>= 32), 2 = 1/8, 1/4, 3/8, 3/16, 1/16 of the batch
   std::atomic<long long> copy_chunk{8};     // host_stream: frames per H2D copy chunk
   std::atomic<long long> walk_stats{0};     // 1 = count live lanes per walk iteration of the tile role ("walk_useful" / "walk_iters" read them back)
   std::atomic<long long> tile_core_cap{0};  // largest tile core edge in pixels; 0 = unlimited
