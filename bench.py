@@ -375,6 +375,10 @@ def main():
             glat = {}
             for label, idx in (("U", 0), ("S", 1), ("F", 2)):
                 fr = d_frames[idx:idx + 1]
+                # un-captured call first: it plans + allocates the workspace the capture then takes out of the pool for good
+                clf.run_cascade_batch_device(fr.data_ptr(), 1, ROWS * COLS, ROWS, COLS, COLS, *PARAMS, 0.0,
+                                             one_out.data_ptr(), cap, one_cnt.data_ptr(), st)
+                torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=stream, capture_error_mode="relaxed"):
                     clf.run_cascade_batch_device(fr.data_ptr(), 1, ROWS * COLS, ROWS, COLS, COLS, *PARAMS, 0.0,

@@ -37,7 +37,9 @@ def main():
     counts = []
 
     variants = [{}, {"tile_warps": 4, "tile_ks": 5, "gather_ks": 7, "tile_tail_min": 33},
-                {"scan_mode": 3, "gather_ks": 4}, {"scan_mode": 1}, {"tile_ni": 2, "tile_warps": 8, "gather_warps": 0, "tile_prefetch": 1}]
+                {"scan_mode": 3, "gather_ks": 4}, {"scan_mode": 1}, {"tile_ni": 2, "tile_warps": 8, "gather_warps": 0, "tile_prefetch": 1},
+                {"tile_head": 2, "tile_warps": 22}, {"tile_head": 1, "tile_warps": 6, "tile_ks": 5, "tile_tail_min": 33},
+                {"host_stream": 1, "copy_chunk": 1, "sub_batch": 1, "deep_flat": 1}, {"host_stream": 0}, {"walk_stats": 1}]
     if args.quick:
         variants = variants[:2]
     keys = sorted({k for v in variants for k in v})
@@ -56,8 +58,13 @@ def main():
         counts += [int(c) for c in cnt]
     for k, val in saved.items():
         pigo_b200.set_option(k, val)
-    for a in (0.3, 0.97):                                                                # rotated: universal gather kernel
+    for a in (0.3, 0.97):                                                                # rotated: table-driven block + deep kernels
         counts.append(len(clf.run_cascade_array(cp_of(sample, 400, 320, 320), a)))
+        dets, cnt = clf.RunCascadeBatch(frames, cp_of(None, 360, 640, 640), a, cap_per_frame=256)
+        counts += [int(c) for c in cnt]
+    pigo_b200.set_option("rot_mode", 1)                                                  # rotated: universal gather kernel
+    counts.append(len(clf.run_cascade_array(cp_of(sample, 400, 320, 320), 0.3)))
+    pigo_b200.set_option("rot_mode", 0)
 
     if not args.quick:
         dets = clf.RunCascade(cp_of(sample, 400, 320, 320), 0.0)
@@ -70,6 +77,24 @@ def main():
         counts.append(sum(1 for f in faces for fc in f if fc.landmarks))
         rgba = np.random.default_rng(0).integers(0, 256, size=(37, 53, 4), dtype=np.uint8)
         counts.append(int(pigo_b200.RgbToGrayscale(rgba).sum()))
+        # device-sequenced pipeline (seed kernels + pair kernel, staged and unstaged, rotated eyes), sharded entry point
+        for stage, ang in ((1, 0.0), (0, 0.0), (1, 0.05)):
+            pigo_b200.set_option("puploc_stage", stage)
+            f, n, p = pipeline.detect_batch_device(clf, plc, flp, frames, cp_of(None, 360, 640, 640), face_cap=16, rng_seed=3, angle=ang, raw=True)
+            counts += [int(n.sum()), int((p["row"] > 0).sum())]
+        pigo_b200.set_option("puploc_stage", 1)
+        pigo_b200.init_devices(1)
+        f, n, p = pipeline.detect_batch_device(clf, plc, flp, frames, cp_of(None, 360, 640, 640), face_cap=16, rng_seed=3, raw=True, sharded=True)
+        counts.append(int(n.sum()))
+        pigo_b200.set_option("puploc_mode", 1)
+        faces2 = pipeline.detect_batch(clf, plc, flp, frames[:1], cp_of(None, 360, 640, 640), iou=0.1)
+        counts.append(sum(len(x) for x in faces2))
+        pigo_b200.set_option("puploc_mode", 0)
+        yy = np.random.default_rng(1).integers(0, 256, size=(21, 40), dtype=np.uint8)
+        cb = np.random.default_rng(2).integers(0, 256, size=(11, 20), dtype=np.uint8)
+        cr = np.random.default_rng(3).integers(0, 256, size=(11, 20), dtype=np.uint8)
+        out, gy = pigo_b200.YCbCrToNRGBA(yy, cb, cr, 2, 37, 21, want_gray=True)
+        counts += [int(out.sum()), int(gy.sum())]
     print("sanitize_run counts:", counts, "launches:", pigo_b200.launch_count() if hasattr(pigo_b200, "launch_count") else "n/a")
 
 
