@@ -54,7 +54,7 @@ struct Options {
   std::atomic<long long> head_back{12};     // dense head: generic phase parks its live windows and returns to the head below this many live lanes
   std::atomic<long long> deep_flat{0};      // deep kernel loop: 0 = groups of a warp fetch together (round 1), 1 = flat (fetch or step per iteration)
   std::atomic<long long> rot_mode{0};       // rotated scan: 0 = table-driven block kernel + deep kernel, 1 = universal gather kernel
-  std::atomic<long long> puploc_stage{1};   // pair kernel: 1 = the current stage's node codes are staged in shared memory
+  std::atomic<long long> puploc_stage{1};   // pair kernel: 0 = all global, 1 = the current stage's node codes staged in shared memory, 2 = + the stage's pixel patch when it fits
   std::atomic<long long> puploc_mode{0};    // RunDetector kernel: 0 = (perturbation, tree)-pair kernel, 1 = warp-per-perturbation kernel
   std::atomic<long long> lanes{1};          // internal streams the groups alternate between
   std::atomic<long long> tile_tail_min{6};  // tail policy threshold

@@ -6,6 +6,7 @@
 // float32 arithmetic uses explicit round-to-nearest intrinsics (and the library is built with
 // -fmad=false): Go on amd64 never fuses r += dr*s (core/puploc.go:149-151).
 #include <algorithm>
+#include <climits>
 
 #include "common.cuh"
 #include "host.h"
@@ -158,6 +159,15 @@ __global__ void __launch_bounds__(1024, 1) puploc_kernel(PuplocTables T, const p
 //   max(0, 65536*int(r) + x) >> 16  ==  max(0, int(r) + (x >> 16))    (rotated variant, see RotNode in common.cuh);
 // seeds with |Scale| > 16384 (products would leave 32 bits) are left to the 64-bit kernel above by the host.
 constexpr int kPairThreads = 512;
+// Sample area of one perturbation in the coming stage: centre +- (|rs|/2 + 1) unrotated ((code*rs) >> 8 with |code| <= 128);
+// rotated: the offsets are (iqc*k0 -+ iqs*k1) >> 16 with iqc, iqs fixed from the INITIAL scale of the perturbation (core/puploc.go:166),
+// so the radius comes from them, not from the current scale.
+__device__ __forceinline__ void box_add(int* box, int ir, int ic, int rs, bool rot, int iqs, int iqc) {
+  const int a = rs < 0 ? -rs : rs;
+  const int h = rot ? (((iqs < 0 ? -iqs : iqs) + (iqc < 0 ? -iqc : iqc)) >> 9) + 2 : (a >> 1) + 2;   // |iqc*k0 - iqs*k1| >> 16 <= (|iqc| + |iqs|) * 128 >> 16
+  atomicMin(&box[0], ir - h); atomicMax(&box[1], ir + h);
+  atomicMin(&box[2], ic - h); atomicMax(&box[3], ic + h);
+}
 // int(r) of core/puploc.go:118, kept inside +-2^30 so that adding a sample offset (|offset| <= |scale|/2 < 2^23, the host
 // rejects larger scales) cannot wrap: anything beyond +-2^30 clamps to the same image border as the exact value would
 __device__ __forceinline__ int clamp_coord(float v) { return max(-(1 << 30), min(1 << 30, (int)v)); }
@@ -167,18 +177,28 @@ __device__ __forceinline__ int clamp_coord(float v) { return max(-(1 << 30), min
 // shared-memory load instead of a lane-divergent global one (ncu round 2, unstaged: L1TEX 71 % busy at 25 sectors per
 // request, issue 47 %); the shared copy skews consecutive trees by 8 bytes, otherwise every tree's node i would sit in the
 // same bank.  The pixel pairs stay global gathers (a landmark seed's patch is up to ~100 KB).
-template <bool STAGED>
-__global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupWork W, unsigned int* __restrict__ counter, int leaf_bytes) {
+// PATCH (with STAGED): before a stage whose sample area -- the bounding box of all perturbations' centres +- scale/2, clamped
+// to the image -- fits `patch_cap` bytes, that area is copied to shared memory with coalesced 16-byte loads and the
+// stage's pixel pairs become shared-memory loads too (a stage gathers 1260 x depth x 2 lane-divergent bytes from it; the
+// scale shrinks by 0.7-0.8 per stage, so the later stages of a landmark call fit).  Stages that do not fit gather from global memory.
+template <bool STAGED, bool PATCH>
+__global__ void __launch_bounds__(kPairThreads, PATCH ? 2 : 3) puploc_pair_kernel(const PupWork W, unsigned int* __restrict__ counter, int leaf_bytes,
+                                                                                 int codes_bytes, int patch_cap) {
   extern __shared__ __align__(16) uint8_t s_dyn[];
   float2* s_leaf = reinterpret_cast<float2*>(s_dyn);     // [63][trees]
   uint8_t* s_codes = s_dyn + leaf_bytes;                 // STAGED: [trees][4L + 8]
+  uint8_t* s_patch = s_codes + codes_bytes;              // PATCH: [rows][pitch]
+  __shared__ int s_box[4];                               // PATCH: min row, max row, min col, max col over the perturbations
   __shared__ float s_r[64], s_c[64], s_s[64];
   __shared__ int s_ir[64], s_ic[64], s_rs[64], s_qs[64], s_qc[64];
   __shared__ unsigned s_item;
   const int tid = threadIdx.x, nt = blockDim.x;
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_item = atomicAdd(counter, 1u);
+    if (tid == 0) {
+      s_item = atomicAdd(counter, 1u);
+      if (PATCH) { s_box[0] = INT_MAX; s_box[1] = INT_MIN; s_box[2] = INT_MAX; s_box[3] = INT_MIN; }
+    }
     __syncthreads();
     const unsigned w = s_item;
     if (w >= (unsigned)W.nwork) break;
@@ -229,8 +249,33 @@ __global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupW
       }
       s_r[tid] = r; s_c[tid] = c; s_s[tid] = s; s_qs[tid] = qs; s_qc[tid] = qc;
       s_ir[tid] = clamp_coord(r); s_ic[tid] = clamp_coord(c); s_rs[tid] = (int)llround((double)s);   // int(r), int(math.Round(float64(s)))
+      if (PATCH && tid < P) box_add(s_box, s_ir[tid], s_ic[tid], s_rs[tid], rot, qs, qc);
     }
     __syncthreads();
+    // PATCH: geometry of the staged sample area of the coming stage (CTA-uniform), see load_patch
+    int p_r0 = 0, p_c0 = 0, p_pitch = 0;
+    bool p_use = false;
+    auto load_patch = [&]() {
+      p_use = false;
+      if (!PATCH || P == 0) return;
+      const int r0 = min(max(s_box[0], 0), rlim), r1 = min(max(s_box[1], 0), rlim);
+      const int c0 = min(max(s_box[2], 0), clim) & ~15, c1 = min(max(s_box[3], 0), clim);
+      const long long rows = (long long)r1 - r0 + 1, pitch = ((long long)c1 - c0 + 16) & ~15ll;
+      if (rows <= 0 || pitch <= 0 || rows * pitch > patch_cap || (W.dim & 15) || (reinterpret_cast<uintptr_t>(pixels) & 15)) return;
+      p_use = true; p_r0 = r0; p_c0 = c0; p_pitch = (int)pitch;
+      const int vec_per_row = (int)(pitch >> 4), total = (int)rows * vec_per_row;
+      for (int q = tid; q < total; q += nt) {
+        const int y = q / vec_per_row, x = q - y * vec_per_row;
+        if (c0 + 16 * x + 16 <= W.dim)     // (vectors past the end of the row are never sampled: columns are clamped to ncols-1 < dim)
+          *reinterpret_cast<uint4*>(s_patch + (size_t)y * pitch + 16 * x) =
+              __ldg(reinterpret_cast<const uint4*>(pixels + (size_t)(r0 + y) * W.dim + c0 + 16 * x));
+      }
+    };
+    load_patch();
+    if (PATCH) {
+      __syncthreads();
+      if (tid == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MIN; s_box[2] = INT_MAX; s_box[3] = INT_MIN; }   // refilled after the stage's sums
+    }
 
     const int npairs = P * T.trees;
     for (int st = 0; st < T.stages; ++st) {
@@ -254,7 +299,9 @@ __global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupW
             const int k3 = flip ? neg_i8(cw >> 24) : (cw >> 24);
             const int r1 = __vimin_s32_relu(ir + ((k0 * rs) >> 8), rlim), r2 = __vimin_s32_relu(ir + ((k2 * rs) >> 8), rlim);   // :118-119
             const int c1 = __vimin_s32_relu(ic + ((k1 * rs) >> 8), clim), c2 = __vimin_s32_relu(ic + ((k3 * rs) >> 8), clim);   // :124/:127
-            const int bit = __ldg(pixels + (size_t)r1 * W.dim + c1) > __ldg(pixels + (size_t)r2 * W.dim + c2) ? 1 : 0;          // :130-136
+            const unsigned q1 = (PATCH && p_use) ? s_patch[(r1 - p_r0) * p_pitch + (c1 - p_c0)] : __ldg(pixels + (size_t)r1 * W.dim + c1);
+            const unsigned q2 = (PATCH && p_use) ? s_patch[(r2 - p_r0) * p_pitch + (c2 - p_c0)] : __ldg(pixels + (size_t)r2 * W.dim + c2);
+            const int bit = q1 > q2 ? 1 : 0;                                                                                     // :130-136
             cw = bit ? kr : kl;
             idx = 2 * idx + 1 + bit;
           }
@@ -270,7 +317,9 @@ __global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupW
             const int c1 = __vimin_s32_relu(ic + (int)((iqs * k0 + iqc * k1) >> 16), clim);   // :189
             const int r2 = __vimin_s32_relu(ir + (int)((iqc * k2 - iqs * k3) >> 16), rlim);   // :190
             const int c2 = __vimin_s32_relu(ic + (int)((iqs * k2 + iqc * k3) >> 16), clim);   // :191
-            const int bit = __ldg(pixels + (size_t)r1 * W.dim + c1) <= __ldg(pixels + (size_t)r2 * W.dim + c2) ? 1 : 0;  // :193-199
+            const unsigned q1 = (PATCH && p_use) ? s_patch[(r1 - p_r0) * p_pitch + (c1 - p_c0)] : __ldg(pixels + (size_t)r1 * W.dim + c1);
+            const unsigned q2 = (PATCH && p_use) ? s_patch[(r2 - p_r0) * p_pitch + (c2 - p_c0)] : __ldg(pixels + (size_t)r2 * W.dim + c2);
+            const int bit = q1 <= q2 ? 1 : 0;                                                                                    // :193-199
             cw = bit ? kr : kl;
             idx = 2 * idx + 1 + bit;
           }
@@ -292,8 +341,14 @@ __global__ void __launch_bounds__(kPairThreads, 3) puploc_pair_kernel(const PupW
         const float s2 = __fmul_rn(s, T.scales);                 // :151
         s_r[tid] = r; s_c[tid] = c; s_s[tid] = s2;
         s_ir[tid] = clamp_coord(r); s_ic[tid] = clamp_coord(c); s_rs[tid] = (int)llround((double)s2);
+        if (PATCH) box_add(s_box, s_ir[tid], s_ic[tid], s_rs[tid], rot, s_qs[tid], s_qc[tid]);
       }
       __syncthreads();
+      if (PATCH && st + 1 < T.stages) {
+        load_patch();
+        __syncthreads();
+        if (tid == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MIN; s_box[2] = INT_MAX; s_box[3] = INT_MIN; }
+      }
     }
     // pool slots >= Perturbs stay 0 (fresh pool object, :228-236); all 63 slots are sorted (:267-269)
     if (tid < 63) {
@@ -324,18 +379,24 @@ int launch_puploc_pairs(const PupWork& W, unsigned int* counter, int num_sms, cu
   }
   const size_t leaf = ((size_t)63 * trees_max * sizeof(float2) + 15) & ~(size_t)15;
   if (leaf > 100 * 1024) return -1;                                   // caller falls back to the warp-per-perturbation kernel
-  const bool staged = g_opt.puploc_stage.load() != 0 && leaf + codes_max <= 110 * 1024;   // two CTAs per SM at least
-  const size_t smem = leaf + (staged ? codes_max : 0);
+  const size_t kBudget = 110 * 1024;                                  // two CTAs per SM at least
+  codes_max = (codes_max + 15) & ~(size_t)15;
+  const bool staged = g_opt.puploc_stage.load() != 0 && leaf + codes_max <= kBudget;
+  size_t patch_cap = 0;
+  if (staged && g_opt.puploc_stage.load() >= 2 && leaf + codes_max + 4096 <= kBudget) patch_cap = std::min<size_t>(48 * 1024, kBudget - leaf - codes_max);
+  const size_t smem = leaf + (staged ? codes_max : 0) + patch_cap;
   static bool attr_set[kMaxDevices] = {};
   int dev = 0; cudaGetDevice(&dev);
   if (!attr_set[dev]) {
-    cudaFuncSetAttribute(puploc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-    cudaFuncSetAttribute(puploc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaFuncSetAttribute(puploc_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBudget);
+    cudaFuncSetAttribute(puploc_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBudget);
+    cudaFuncSetAttribute(puploc_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBudget);
     attr_set[dev] = true;
   }
   const int grid = max(1, min(W.nwork, num_sms * 3));
-  if (staged) puploc_pair_kernel<true><<<grid, kPairThreads, smem, st>>>(W, counter, (int)leaf);
-  else puploc_pair_kernel<false><<<grid, kPairThreads, smem, st>>>(W, counter, (int)leaf);
+  if (patch_cap > 0) puploc_pair_kernel<true, true><<<grid, kPairThreads, smem, st>>>(W, counter, (int)leaf, (int)codes_max, (int)patch_cap);
+  else if (staged) puploc_pair_kernel<true, false><<<grid, kPairThreads, smem, st>>>(W, counter, (int)leaf, (int)codes_max, 0);
+  else puploc_pair_kernel<false, false><<<grid, kPairThreads, smem, st>>>(W, counter, (int)leaf, 0, 0);
   return 0;
 }
 

@@ -562,7 +562,7 @@ def test_host_frames_streamed_behind_the_copy(gpu_face, oracle_face, restore_rou
         assert cnt[f] == len(o) and dets[f, :cnt[f]].tobytes() == o.tobytes()
 
 
-@pytest.mark.parametrize("mode,stage", [(0, 1), (0, 0), (1, 0)])
+@pytest.mark.parametrize("mode,stage", [(0, 2), (0, 1), (0, 0), (1, 0)])
 def test_puploc_kernels_agree_with_oracle(sample_gray, restore_round2_options, mode, stage):
     """Both RunDetector kernels ((perturbation, tree)-pair kernel and warp-per-perturbation kernel), rotated and not,
     flips, Perturbs 0..63, seeds near and beyond the image border, on a frame batch."""
@@ -625,12 +625,13 @@ def _check_pipeline_against_oracle(got, frames, rows, cols, oracle_face, oplc, o
     return nrefined
 
 
-@pytest.mark.parametrize("angle", [0.0, 0.03])
-def test_device_pipeline_vs_oracle(gpu_face, oracle_face, sample_gray, angle):
+@pytest.mark.parametrize("angle,stage", [(0.0, 1), (0.03, 1), (0.0, 2), (0.03, 2)])
+def test_device_pipeline_vs_oracle(gpu_face, oracle_face, sample_gray, restore_round2_options, angle, stage):
     """pigo_detect_batch: the whole face -> cluster -> eye seeds -> RunDetector x2 -> landmark seeds ->
     15 x RunDetector sequence on the device in one call, replayed step by step on the CPU oracle with the same injected
     randoms (core/flploc_test.go:75-154; angle > 0 like cmd/pigo/main.go:422 passes det.angle to the eye RunDetector)."""
     from pigo_b200 import pipeline
+    pigo_b200.set_option("puploc_stage", stage)
     plc, flp, oplc, oflp = _pipeline_cascades()
     frames = np.stack([synth.frame_faces(sample_gray, 540, 960, shift=(40 * i, 25 * i), noise_seed=30 + i) for i in range(3)] +
                       [synth.frame_noise(540, 960, 5)])
