@@ -1,5 +1,6 @@
 // common.cuh -- shared device/host structures of libpigo_b200 (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -160,9 +161,16 @@ struct TiledArgs {
   int32_t head_trees;                     // 0 = classic kernel
   int32_t head_nscales;                   // ladder entries [0, head_nscales) are tiled
   uint32_t head_off, ring_off, tiles_off;
+  int32_t use_tmap;                       // tile fill: 1 = one 3-D TMA tensor copy per tile (TileMaps), 0 = one bulk copy per tile row
   int32_t gather_limit;                   // gather role: trees a window walks here before it is handed to the deep kernel (<= ks)
   unsigned long long* stats;              // developer counter (option walk_stats): [0] += live lanes, [1] += 1 per tile-role walk iteration
   int32_t head_back;                      // generic phase: with an empty ring and fewer live lanes than this, park them in the ring and go back to the head
+};
+
+// TMA descriptors of the frame batch, one per tile band (the box = the band's tile: pitch x rows_t x 1 frame), passed to the
+// fused kernels as a __grid_constant__ parameter.
+struct TileMaps {
+  CUtensorMap m[kMaxBands];
 };
 
 __device__ __constant__ int c_qcos[33] = {256, 251, 236, 212, 181, 142, 97, 49, 0, -49, -97, -142, -181, -212, -236, -251, -256,

@@ -246,6 +246,34 @@ long long walk_stats_query(int which) {
   return total;
 }
 
+// ---- TMA descriptors of the frame batch (one per tile band) ------------------------------------------------------------
+// cuTensorMapEncodeTiled comes from the driver library; it is looked up through the runtime (no link dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// frames [nframes][rows][dim] u8 (frames `frame_stride` bytes apart) as a 3-D tensor; box = one tile of band B
+static bool encode_tile_map(CUtensorMap* m, const ScanArgs& A, const TileBand& B) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || B.pitch > 256 || B.rows_t > 256 || (A.dim % 16) || (A.frame_stride % 16) || ((uintptr_t)A.frames % 16)) return false;
+  const cuuint64_t gdim[3] = {(cuuint64_t)A.dim, (cuuint64_t)A.rows, (cuuint64_t)A.nframes};
+  const cuuint64_t gstride[2] = {(cuuint64_t)A.dim, (cuuint64_t)A.frame_stride};
+  const cuuint32_t box[3] = {(cuuint32_t)B.pitch, (cuuint32_t)B.rows_t, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)A.frames, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_err(PIGO_E_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
@@ -360,8 +388,12 @@ int run_scan(FaceReplica* c, Workspace* w, int lane, ScanArgs& A, unsigned long 
       long long grid = num_sms;
       if (Wg == 0) grid = std::max<long long>(1, std::min<long long>(num_sms, (long long)((F.total_tiles + W - 1) / W)));
       const size_t smem = P.L.tiles_off + (size_t)P.L.tile_bytes * W;
+      TileMaps TM{};
+      F.use_tmap = (F.aligned && g_opt.tile_tmap.load() != 0) ? 1 : 0;
+      for (int b = 0; b < tp.nbands && F.use_tmap; ++b)
+        if (!encode_tile_map(&TM.m[b], A, tp.band[b])) F.use_tmap = 0;
       timing_begin(T_TILED, st);
-      launch_scan_tiled(F, (int)grid, (W + Wg) * 32, smem, P.ni, st);
+      launch_scan_tiled(F, TM, (int)grid, (W + Wg) * 32, smem, P.ni, st);
       timing_end(T_TILED, st);
       g_launches++;
       if ((rc = check_launch("fused scan"))) return rc;

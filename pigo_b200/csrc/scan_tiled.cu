@@ -41,6 +41,13 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
                "r"(bytes), "r"(bar)
                : "memory");
 }
+// One tile = one 3-D tensor copy (x = byte column, y = row, z = frame); out-of-frame parts of the box are zero-filled and
+// count towards the transaction bytes, so the barrier always expects the whole box.
+__device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(256, MINB) scan_gather2_kernel(const TiledArgs
 }
 
 template <int NI, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) {
+__global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A, const __grid_constant__ TileMaps TM) {
   extern __shared__ __align__(128) uint8_t smem[];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -412,7 +419,15 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
 
     // ---- fill the tile: rows [gy0, gy0+rows_t) x bytes [gx0, gx0+pitch) clipped to the frame
     __syncwarp();
-    if (A.aligned) {
+    if (A.use_tmap) {
+      // ONE TMA tensor copy per tile (3-D box pitch x rows_t x 1 frame, zero fill outside the frame), issued by lane 0
+      if (lane == 0) {
+        mbar_expect_tx(wbar, (uint32_t)(B.rows_t * pitch));
+        tma_tile_g2s(smem_base + my_tile, &TM.m[b], gx0, gy0, frame, wbar);
+      }
+      mbar_wait(wbar, tile_phase);
+      tile_phase ^= 1u;
+    } else if (A.aligned) {
       // one TMA bulk copy per tile row (16-byte aligned, clipped to the frame), completion on the warp's mbarrier
       const int y_lo = max(gy0, 0), y_hi = min(gy0 + B.rows_t, S.rows);
       const int x_lo = max(gx0, 0), x_hi = min(gx0 + pitch, S.dim);
@@ -696,7 +711,7 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A) 
 // ring entry (kRingEntry = 12 bytes): pb (18 bits) | tree (6) | scale (8);  wid;  acc
 
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) scan_head_kernel(const TiledArgs A) {
+__global__ void __launch_bounds__(MAXT, 1) scan_head_kernel(const TiledArgs A, const __grid_constant__ TileMaps TM) {
   extern __shared__ __align__(128) uint8_t smem[];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -777,7 +792,14 @@ __global__ void __launch_bounds__(MAXT, 1) scan_head_kernel(const TiledArgs A) {
     if (!__any_sync(FULL, sc_n > 0)) continue;
 
     __syncwarp();
-    if (A.aligned) {
+    if (A.use_tmap) {
+      if (lane == 0) {
+        mbar_expect_tx(wbar, (uint32_t)(B.rows_t * pitch));
+        tma_tile_g2s(smem_base + my_tile, &TM.m[b], gx0, gy0, frame, wbar);
+      }
+      mbar_wait(wbar, tile_phase);
+      tile_phase ^= 1u;
+    } else if (A.aligned) {
       const int y_lo = max(gy0, 0), y_hi = min(gy0 + B.rows_t, S.rows);
       const int x_lo = max(gx0, 0), x_hi = min(gx0 + pitch, S.dim);
       const uint32_t row_bytes = (uint32_t)(x_hi - x_lo);
@@ -981,9 +1003,9 @@ __global__ void __launch_bounds__(MAXT, 1) scan_head_kernel(const TiledArgs A) {
 }
 
 template <int NI, int MAXT>
-static void launch_tiled_ni(const TiledArgs& A, int grid, int threads, size_t smem, cudaStream_t st) {
+static void launch_tiled_ni(const TiledArgs& A, const TileMaps& TM, int grid, int threads, size_t smem, cudaStream_t st) {
   cudaFuncSetAttribute(scan_tiled_kernel<NI, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  scan_tiled_kernel<NI, MAXT><<<grid, threads, smem, st>>>(A);
+  scan_tiled_kernel<NI, MAXT><<<grid, threads, smem, st>>>(A, TM);
 }
 
 static const void* gather2_fn(int ng, bool rot) {
@@ -1008,17 +1030,17 @@ int gather2_ctas_per_sm(size_t smem, int ng, bool rot) {
 
 int tiled_max_threads(int ni) { return ni == 1 ? 1024 : (ni == 2 ? 768 : 512); }
 
-void launch_scan_tiled(const TiledArgs& A, int grid, int threads, size_t smem, int ni, cudaStream_t st) {
+void launch_scan_tiled(const TiledArgs& A, const TileMaps& TM, int grid, int threads, size_t smem, int ni, cudaStream_t st) {
   if (A.head_trees > 0) {
     cudaFuncSetAttribute(scan_head_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    scan_head_kernel<1024><<<grid, threads, smem, st>>>(A);
+    scan_head_kernel<1024><<<grid, threads, smem, st>>>(A, TM);
     return;
   }
   switch (ni) {
-    case 1: launch_tiled_ni<1, 1024>(A, grid, threads, smem, st); break;
-    case 2: launch_tiled_ni<2, 768>(A, grid, threads, smem, st); break;
-    case 3: launch_tiled_ni<3, 512>(A, grid, threads, smem, st); break;
-    default: launch_tiled_ni<4, 512>(A, grid, threads, smem, st); break;
+    case 1: launch_tiled_ni<1, 1024>(A, TM, grid, threads, smem, st); break;
+    case 2: launch_tiled_ni<2, 768>(A, TM, grid, threads, smem, st); break;
+    case 3: launch_tiled_ni<3, 512>(A, TM, grid, threads, smem, st); break;
+    default: launch_tiled_ni<4, 512>(A, TM, grid, threads, smem, st); break;
   }
 }
 
