@@ -89,6 +89,7 @@ int pigo_init(int device);
  * replicated on a device at first use there.  Enables peer access between the selected devices. */
 int pigo_init_devices(unsigned device_mask);
 int pigo_device_count(void);
+/* Waits for outstanding work and frees the library-owned scratch that belongs to no handle (handles stay valid). */
 int pigo_shutdown(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t pigo_launch_count(void);

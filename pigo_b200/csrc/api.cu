@@ -570,7 +570,8 @@ int pigo_device_count(void) {
   return n;
 }
 
-int pigo_shutdown(void) { return PIGO_OK; }
+int pigo_shutdown_impl(void);
+int pigo_shutdown(void) { return pigo_shutdown_impl(); }
 
 int pigo_alloc_pinned(void** ptr, size_t bytes) {
   if (!ptr) return set_err(PIGO_E_INVALID, "null ptr");
@@ -726,6 +727,24 @@ int pigo_run_cascade_batch_sharded(const pigo_cascade* cc, const uint8_t* frames
 
 // ---- ClusterDetections ---------------------------------------------------------------------------------
 static WorkspacePool g_misc_pool[kMaxDevices];   // scratch of the handle-less entry points (cluster, grayscale, ycbcr), per device
+
+// pigo_shutdown: waits for the devices in use and releases the library-owned scratch that is not tied to a handle (cached
+// workspaces of the handle-less entry points).  Handles stay valid -- their own scratch goes with pigo_*_destroy -- and the
+// library can be used again afterwards.
+int pigo_shutdown_impl(void) {
+  for (int d = 0; d < kMaxDevices; ++d) {
+    if (device_sms(d) == 148 && g_misc_pool[d].free_list.empty()) continue;
+    if (g_misc_pool[d].free_list.empty()) continue;
+    if (cudaSetDevice(d) != cudaSuccess) { cudaGetLastError(); continue; }
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> g(g_misc_pool[d].mu);
+    for (auto* w : g_misc_pool[d].free_list) delete w;
+    g_misc_pool[d].free_list.clear();
+  }
+  const int dev = g_device.load();
+  if (dev >= 0) cudaSetDevice(dev);
+  return PIGO_OK;
+}
 
 static int cluster_batch_on(int dev, pigo_det* dets, const int* n, int nframes, int cap_per_frame, double iou_threshold, pigo_det* out,
                             int out_cap_per_frame, int* n_out, unsigned flags, void* stream_) {

@@ -73,10 +73,6 @@ __device__ __forceinline__ int ceil_div_pos(int num, int den) { return num <= 0 
 
 
 
-// shared-memory loads by 32-bit shared-window address (what __cvta_generic_to_shared yields)
-__device__ __forceinline__ int lds_b32(uint32_t a) { int v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-
 // sign-extended byte k of a packed code word: one PRMT (selector nibble with bit 3 set replicates the sign)
 // (prmt.b32 default mode; __byte_perm() documents only 3 selector bits, so the PTX instruction is spelled out)
 __device__ __forceinline__ int sx0(int w) { int r; asm("prmt.b32 %0, %1, 0, 0x8880;" : "=r"(r) : "r"(w)); return r; }
@@ -590,15 +586,14 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A, 
           }
         } else {
           // Plain walk: one 32-bit node load per level (fewest shared-memory wavefronts; the kernel is L1TEX-bound).
-          // Explicit 32-bit shared-window addresses (record and centre pixel made absolute once per tree) and the byte offset
-          // 4*idx carried instead of idx: ~3 instructions less per level than indexing smem[] (ncu source page, round 2).
-          uint32_t ta[NI], pa[NI], off[NI];
+          // (Round 2 tried explicit 32-bit shared-window addresses via inline ld.shared and a byte-offset index -- about three
+          // instructions less per level on paper -- and measured 2 % SLOWER: the volatile asm loads pin the schedule.)
 #pragma unroll
-          for (int u = 0; u < NI; ++u) { ta[u] = smem_base + tbo[u]; pa[u] = smem_base + pb[u]; off[u] = 4; }
+          for (int u = 0; u < NI; ++u) idx[u] = 1;
 #pragma unroll
           for (int j = 0; j < 6; ++j) {
 #pragma unroll
-            for (int u = 0; u < NI; ++u) cw[u] = lds_b32(ta[u] + off[u]);
+            for (int u = 0; u < NI; ++u) cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4 * idx[u]);
             uint32_t p1[NI], p2[NI];
 #pragma unroll
             for (int u = 0; u < NI; ++u) {
@@ -606,21 +601,21 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A, 
               const int s = sv[u];
               const int o1 = ((sx0(cw[u]) * s) >> 8) * pitch + ((sx1(cw[u]) * s) >> 8);
               const int o2 = ((sx2(cw[u]) * s) >> 8) * pitch + ((sx3(cw[u]) * s) >> 8);
-              p1[u] = lds_u8(pa[u] + o1);
-              p2[u] = lds_u8(pa[u] + o2);
+              p1[u] = smem[pb[u] + o1];
+              p2[u] = smem[pb[u] + o2];
             }
 #pragma unroll
-            for (int u = 0; u < NI; ++u) off[u] = 2 * off[u] + (p1[u] <= p2[u] ? 4u : 0u);   // idx = 2*idx + bit, core/pigo.go:129-135
+            for (int u = 0; u < NI; ++u) idx[u] = 2 * idx[u] + (p1[u] <= p2[u] ? 1 : 0);   // core/pigo.go:129-135
           }
 #pragma unroll
-          for (int u = 0; u < NI; ++u) { cw[u] = lds_b32(ta[u] + off[u]); idx[u] = (int)(off[u] >> 2); }   // leaf (words 64..127)
+          for (int u = 0; u < NI; ++u) cw[u] = *reinterpret_cast<const int*>(smem + tbo[u] + 4 * idx[u]);   // leaf (words 64..127)
         }
         bool hit = false;
         float thr_last[NI];
 #pragma unroll
         for (int u = 0; u < NI; ++u) {
           const float pred = __int_as_float(cw[u]);         // after the last level the selected "child" is the leaf value
-          const float thr = __int_as_float(lds_b32(smem_base + tbo[u] + 512));
+          const float thr = *reinterpret_cast<const float*>(smem + tbo[u] + 512);
           thr_last[u] = thr;
           acc[u] += pred;                                   // core/pigo.go:137 (float32, tree order)
           alive[u] = alive[u] && !(acc[u] <= thr);          // :139-141
