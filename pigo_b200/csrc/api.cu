@@ -254,8 +254,9 @@ static int build_plan(int rows, int cols, int min_size, int max_size, double shi
 using namespace pigo;
 
 // Frames per pipeline group of one batch call.  Resident frames: uniform groups of 128 (fewest kernel tails; the deferred
-// queues of a group stay bounded).  Host frames without in-kernel waiting: 64.  Host frames streamed behind the copy
-// (host_stream): uniform 128 by default.  PCIe (50.7 GB/s measured: 10.5 ms for 256 x 1080p) and the scan (10.4 ms) run at
+// queues of a group stay bounded).  Host frames: 64, with or without in-kernel waiting (host_stream): with it the fused kernel
+// of a group is copy-bound and ends when the group's last chunk arrives, and the group's tail kernels then overlap the next
+// group's copy.  PCIe (49-51 GB/s measured: 10.5-10.8 ms for 256 x 1080p) and the scan (10.4 ms) run at
 // the same rate, so a step costs about  [time the scan idles behind the first copy chunks] + [scan]  and also at least
 // [copy] + [tail kernels of the last group]; stream_taper = 1 (128, then half of the rest) shortens the second term but
 // its small groups lengthen the first (measured 13.2 vs 12.6 ms); stream_taper = 2 (1/8, 1/4, 3/8, 3/16, 1/16 of the batch)
@@ -283,7 +284,7 @@ static std::vector<int> group_schedule(int nframes, bool resident, bool streamed
     if (left > 0) g.push_back(left);
     return g;
   }
-  if (sub <= 0) sub = (resident || streamed) ? 128 : 64;
+  if (sub <= 0) sub = resident ? 128 : 64;   // streamed host frames: 64 measured best (12.0 vs 12.5 ms with 128: a group's tail kernels overlap the next group's chunks)
   for (int left = nframes; left > 0; left -= (int)sub) g.push_back((int)std::min<long long>(sub, left));
   return g;
 }
