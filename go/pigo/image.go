@@ -53,29 +53,28 @@ func ImgToNRGBA(img image.Image) *image.NRGBA {
 	if dstW == 0 || dstH == 0 {
 		return dst
 	}
+	// *image.YCbCr (what a JPEG decodes to): the per-pixel conversion runs on the GPU.  Negative rectangle origins keep the
+	// reference's own loop below (Go's x/2 truncates toward zero, the library's chroma indexing assumes origins >= 0).
+	if src, ok := img.(*image.YCbCr); ok && srcBounds.Min.X >= 0 && srcBounds.Min.Y >= 0 {
+		yo, co := src.YOffset(srcBounds.Min.X, srcBounds.Min.Y), src.COffset(srcBounds.Min.X, srcBounds.Min.Y)
+		if _, err := call(func() C.int {
+			return C.pigo_ycbcr_to_nrgba((*C.uint8_t)(unsafe.Pointer(&src.Y[yo])), (*C.uint8_t)(unsafe.Pointer(&src.Cb[co])),
+				(*C.uint8_t)(unsafe.Pointer(&src.Cr[co])), C.int(src.YStride), C.int(src.CStride), C.int(src.SubsampleRatio),
+				C.int(srcBounds.Min.X), C.int(srcBounds.Min.Y), C.int(dstW), C.int(dstH), (*C.uint8_t)(unsafe.Pointer(&dst.Pix[0])), nil,
+				C.PIGO_MEM_HOST, nil)
+		}); err != nil {
+			panic(err)
+		}
+		return dst
+	}
 	switch src := img.(type) {
 	case *image.NRGBA:
 		for y := 0; y < dstH; y++ { // row copy, core/image.go:52-59
 			si := src.PixOffset(srcBounds.Min.X, srcBounds.Min.Y+y)
 			copy(dst.Pix[y*dst.Stride:y*dst.Stride+dstW*4], src.Pix[si:si+dstW*4])
 		}
-	case *image.YCbCr:
-		if srcBounds.Min.X >= 0 && srcBounds.Min.Y >= 0 {
-			// the planes as the library expects them: Y from the rectangle origin, chroma from COffset(Min)
-			yo, co := src.YOffset(srcBounds.Min.X, srcBounds.Min.Y), src.COffset(srcBounds.Min.X, srcBounds.Min.Y)
-			if _, err := call(func() C.int {
-				return C.pigo_ycbcr_to_nrgba((*C.uint8_t)(unsafe.Pointer(&src.Y[yo])), (*C.uint8_t)(unsafe.Pointer(&src.Cb[co])),
-					(*C.uint8_t)(unsafe.Pointer(&src.Cr[co])), C.int(src.YStride), C.int(src.CStride), C.int(src.SubsampleRatio),
-					C.int(srcBounds.Min.X), C.int(srcBounds.Min.Y), C.int(dstW), C.int(dstH), (*C.uint8_t)(unsafe.Pointer(&dst.Pix[0])), nil,
-					C.PIGO_MEM_HOST, nil)
-			}); err != nil {
-				panic(err)
-			}
-			return dst
-		}
-		fallthrough // negative origins: Go's x/2 truncates toward zero, keep the reference's own loop semantics
 	default:
-		for y := 0; y < dstH; y++ { // core/image.go:77-88
+		for y := 0; y < dstH; y++ { // core/image.go:77-88 (and :60-76 for YCbCr images with a negative origin: color.NRGBAModel goes through YCbCrToRGB too)
 			di := dst.PixOffset(0, y)
 			for x := 0; x < dstW; x++ {
 				c := color.NRGBAModel.Convert(img.At(srcBounds.Min.X+x, srcBounds.Min.Y+y)).(color.NRGBA)

@@ -284,8 +284,15 @@ static std::vector<int> group_schedule(int nframes, bool resident, bool streamed
     if (left > 0) g.push_back(left);
     return g;
   }
+  const bool auto_sub = sub <= 0;
   if (sub <= 0) sub = resident ? 128 : 64;   // streamed host frames: 64 measured best (12.0 vs 12.5 ms with 128: a group's tail kernels overlap the next group's chunks)
   for (int left = nframes; left > 0; left -= (int)sub) g.push_back((int)std::min<long long>(sub, left));
+  if (auto_sub && streamed && taper == 3 && g.size() >= 2 && g.back() >= 32) {
+    // the step ends one group's tail kernels after the last chunk: halve the LAST group only
+    const int n = g.back();
+    g.back() = n - n / 2;
+    g.push_back(n / 2);
+  }
   return g;
 }
 
