@@ -343,13 +343,19 @@ int run_scan(FaceReplica* c, Workspace* w, int lane, ScanArgs& A, unsigned long 
   T.gather_blocks_per_frame = 0;
   T.tile_prefetch = g_opt.tile_prefetch.load() ? 1 : 0;
   T.gather_ni = (int)std::min<long long>(std::max<long long>(1, g_opt.gather_ni.load()), 3);
-  // latency mode (a frame or two): gather-role windows leave for the deep kernel after a few trees
+  // how long a gather-role window stays in the fused kernel before it leaves for the deep kernel (which walks a window with a
+  // lane group and is the cheaper place for long walks).  Measured (profiles/sweeps_r02.txt, "gather_limit"): up to ~32 1080p
+  // frames per call leaving after 8 trees is 10-35 % faster end to end, from 64 frames on 24 trees is best by ~2 %.
   long long glimit = g_opt.gather_limit.load();
-  if (glimit <= 0) glimit = A.batch_frames <= 4 ? 8 : (1 << 20);
+  const unsigned long long call_windows = (unsigned long long)A.wins_per_frame * (unsigned long long)std::max(1, A.batch_frames);
+  // "small call" = at most 4 M windows in the whole API call (a 1080p frame has 0.9 M, a 4K frame 3.7 M): latency matters, not throughput
+  const bool small_call = call_windows <= 4000000ull;
+  // (the rotated scan has no fused kernel: its block kernel keeps 24 trees unless the call is small, 8 costs it up to 40 %)
+  if (glimit <= 0) glimit = (rot ? small_call : call_windows <= 40000000ull) ? 8 : 24;
   T.gather_limit = (int)std::min<long long>(glimit, 1 << 20);
   // small batches (a frame or two) cannot fill the GPU with 256-window blocks: use 64-window blocks then
   // (decided from the frames of the whole API call, not of this pipeline group: the block prefix lives in the shared plan)
-  T.gb_shift = (g_opt.gather_block.load() == 8 || (g_opt.gather_block.load() == 0 && A.batch_frames <= 4)) ? 3 : 4;
+  T.gb_shift = (g_opt.gather_block.load() == 8 || (g_opt.gather_block.load() == 0 && small_call)) ? 3 : 4;
 
   // ---- fused kernel: tile warps over the small scales (+ optional gather warps over the rest)
   auto round_ks = [&](long long v) {
@@ -436,7 +442,7 @@ int run_scan(FaceReplica* c, Workspace* w, int lane, ScanArgs& A, unsigned long 
   {
     timing_begin(T_DEEP, st);
     int group = (int)g_opt.deep_group.load();
-    if (group != 8 && group != 16 && group != 32) group = A.batch_frames <= 4 ? 32 : 8;   // few frames: latency of a full survivor matters
+    if (group != 8 && group != 16 && group != 32) group = small_call ? 32 : 8;   // small call: the latency of a full survivor matters
     launch_deep(A, d_work + 3, num_sms * 8, group, st);
     timing_end(T_DEEP, st);
     g_launches++;
