@@ -336,6 +336,7 @@ static int scan_batch_on(pigo_cascade* c, int dev, const uint8_t* frames, int nf
     CUDA_TRY(cudaStreamSynchronize(st));  // plan_host may be rebuilt by the next call before the copy ran
     w->pad_first_untiled = -1;
     w->rot_slot = -1;
+    w->ptab_sig.clear();
     w->p_rows = rows; w->p_cols = cols; w->p_min = min_size; w->p_max = max_size; w->p_shift = shift_factor; w->p_scale = scale_factor;
   }
   const int nscales = (int)w->plan_host.size();

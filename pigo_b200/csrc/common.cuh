@@ -164,6 +164,14 @@ struct TiledArgs {
   int32_t use_tmap;                       // tile fill: 1 = one 3-D TMA tensor copy per tile (TileMaps), 0 = one bulk copy per tile row
   int32_t gather_limit;                   // gather role: trees a window walks here before it is handed to the deep kernel (<= ks)
   unsigned long long* stats;              // developer counter (option walk_stats): [0] += live lanes, [1] += 1 per tile-role walk iteration
+  // per-scale offset tables (scan_ptab_kernel): ptab = [tiled ladder entries][ptab_stride bytes] records of kTreeRec bytes for the
+  // first kt trees; rounds = groups of tile_warps consecutive tiles of ONE band, strided statically over the CTAs
+  const uint8_t* ptab;
+  int32_t kt;                             // trees per table (0 = classic kernel)
+  uint32_t ptab_stride;                   // bytes per ladder entry in ptab (kt * kTreeRec rounded up to 16)
+  uint32_t ptab_off;                      // shared-memory offset of the two table buffers (ptab_stride + 16 bytes apart)
+  uint32_t rounds_per_frame;
+  uint32_t band_rounds[kMaxBands];
   int32_t head_back;                      // generic phase: with an empty ring and fewer live lanes than this, park them in the ring and go back to the head
 };
 
@@ -192,6 +200,52 @@ __device__ __forceinline__ int find_scale(const ScaleEntry* __restrict__ plan, i
     if (__ldg(&plan[mid].wbase) <= wid) lo = mid; else hi = mid - 1;
   }
   return lo;
+}
+
+// ---- mbarrier + TMA helpers (bulk copy of cascade records, tensor copy of pixel tiles) ---------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+// One tile = one 3-D tensor copy (x = byte column, y = row, z = frame); out-of-frame parts of the box are zero-filled and
+// count towards the transaction bytes, so the barrier always expects the whole box.
+__device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+// non-blocking test of a barrier phase
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
 }
 
 }  // namespace pigo

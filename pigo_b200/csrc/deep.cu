@@ -9,6 +9,8 @@
 // Round 2: (1) queue items carry their ladder entry, so the consumer needs no binary search; (2) ROT variant:
 // classifyRotatedRegion (core/pigo.go:150-191) with the node's sample offsets read from the per-call table (RotNode,
 // common.cuh) instead of being recomputed per node; (3) a flat-loop variant (deep_flat=1), measured and left off.
+#include <algorithm>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -128,6 +130,122 @@ __global__ void __launch_bounds__(256) deep_kernel(const ScanArgs A, unsigned lo
       }
     }
   }
+}
+
+// Shared-memory variant (unrotated, large calls): ONE CTA PER SM keeps the tree records [t_lo, t_lo + ktrees) of the tiled table
+// (kTreeRec bytes each: codes, leaves, threshold -- the layout the fused kernel stages) in its 227 KB of shared memory, filled by
+// the TMA bulk engine.  A walk then costs two pixel gathers per level through L1TEX instead of two gathers plus a divergent
+// 64-bit node load: the kernel is bound by L1TEX sectors (ncu r02g: 86 %), and a third of them were node loads.  Consecutive
+// trees sit 130 words apart, so the GROUP lanes of a window (consecutive trees, same node index at the root) read distinct banks.
+// Trees below t_lo (thin-tail handoffs of the tile warps, latency-mode items) take the global path of deep_walk.
+__device__ __forceinline__ float deep_walk_smem(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ pc, int s, int dim) {
+  int idx = 1;
+  int cw = *reinterpret_cast<const int*>(rec + 4);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int2 kids = *reinterpret_cast<const int2*>(rec + 8 * idx);   // children codes, or the two leaves after the last level
+    const int o1 = (((int)(int8_t)(cw) * s) >> 8) * dim + (((int)(int8_t)(cw >> 8) * s) >> 8);
+    const int o2 = (((int)(int8_t)(cw >> 16) * s) >> 8) * dim + (((cw >> 24) * s) >> 8);
+    const unsigned p1 = __ldg(pc + o1), p2 = __ldg(pc + o2);
+    const bool right = p1 <= p2;                  // core/pigo.go:129-135
+    cw = right ? kids.y : kids.x;
+    idx = 2 * idx + (right ? 1 : 0);
+  }
+  return __int_as_float(cw);
+}
+
+constexpr uint32_t kDeepRecOff = 16;   // the mbarrier lives in the first 16 bytes
+
+template <int GROUP>
+__global__ void __launch_bounds__(1024) deep_smem_kernel(const ScanArgs A, unsigned long long* counter, const uint8_t* __restrict__ tab,
+                                                            int t_lo, int ktrees) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(dsm);
+  const uint32_t bytes = (uint32_t)ktrees * (uint32_t)kTreeRec;    // ktrees and t_lo are even: 16-byte multiples / alignment
+  const FaceTables T = A.tab;
+  const uint32_t qn = min(*A.long_count, A.long_cap);
+  if (qn == 0) return;
+  if (threadIdx.x == 0) mbar_init(base, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(base, bytes);
+    for (uint32_t off = 0; off < bytes; off += 32768u)
+      tma_bulk_g2s(base + kDeepRecOff + off, tab + (size_t)t_lo * kTreeRec + off, min(32768u, bytes - off), base);
+  }
+  __syncthreads();
+  mbar_wait(base, 0);
+
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (GROUP - 1);
+  const unsigned gmask = GROUP == 32 ? 0xffffffffu : (GROUP == 16 ? (0xffffu << (lane & 16)) : (GROUP == 8 ? (0xffu << (lane & 24)) : (0xfu << (lane & 28))));
+  const int leader = lane & ~(GROUP - 1);
+  const int t_hi = t_lo + ktrees;
+  for (;;) {
+    unsigned long long g = 0;
+    if (sub == 0) g = atomicAdd(counter, 1ull);
+    g = __shfl_sync(gmask, g, leader);
+    if (g >= qn) break;
+    const DeepWin w = deep_fetch<0>(A, T, g);
+    int t0 = w.t0;
+    float acc = w.acc;
+    bool rejected = false;
+    float thr_prev = 0.f;
+    while (t0 < T.ntrees && !rejected) {
+      const int t = min(t0 + sub, T.ntrees - 1);      // lanes past the last tree redo it harmlessly
+      float thr, pred;
+      if (t >= t_lo && t < t_hi) {
+        const uint8_t* rec = dsm + kDeepRecOff + (uint32_t)(t - t_lo) * (uint32_t)kTreeRec;
+        thr = *reinterpret_cast<const float*>(rec + 512);
+        pred = deep_walk_smem(rec, w.pc, w.s, A.dim);
+      } else {
+        thr = __ldg(T.thresh + t);
+        pred = deep_walk<0>(A, T, w.pc, w.rt, t, w.r, w.c, w.s, 0);
+      }
+      const int nvalid = min(GROUP, T.ntrees - t0);
+      for (int j = 0; j < nvalid; ++j) {              // the reference's sequential accumulation, :137-141
+        acc += __shfl_sync(gmask, pred, leader + j);
+        thr_prev = __shfl_sync(gmask, thr, leader + j);
+        if (acc <= thr_prev) { rejected = true; break; }
+      }
+      t0 += GROUP;
+    }
+    if (!rejected && sub == 0) {
+      const float q = acc - thr_prev;                 // :144
+      if (q > 0.0f) {                                 // :246
+        const int pos = atomicAdd(A.raw_count + w.frame, 1);
+        if (pos < A.cap) A.raw[(size_t)w.frame * A.cap + pos] = RawDet{w.wid, q};
+      }
+    }
+  }
+}
+
+// Resident range [t_lo, t_lo + k): t_lo and k even (16-byte alignment / size of the bulk copy), clipped to the cascade and to what
+// one CTA's shared memory holds.  The launch puts as many CTAs on an SM as the range allows: a smaller range leaves more of the
+// 256 KB L1/shared array to the L1 cache, which the pixel gathers live on (measured: all 446 trees resident = 2x SLOWER).
+static constexpr size_t kDeepSmemMax = 232448;
+void launch_deep_smem(const ScanArgs& A, unsigned long long* counter, const uint8_t* tab_tiled, int num_sms, int threads, int group,
+                      int t_lo, int k, cudaStream_t st) {
+  const int ntrees = A.tab.ntrees;
+  t_lo = std::max(0, std::min(t_lo, ntrees - 2)) & ~1;
+  k = std::min(k, (int)((kDeepSmemMax - kDeepRecOff) / kTreeRec));
+  k = std::max(2, std::min(k, ntrees - t_lo)) & ~1;
+  const size_t smem = kDeepRecOff + (size_t)k * kTreeRec;
+#define PIGO_DEEP_SMEM(G)                                                                                              \
+  do {                                                                                                                 \
+    cudaFuncSetAttribute(deep_smem_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+    int per_sm = 1;                                                                                                    \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, deep_smem_kernel<G>, threads, smem) != cudaSuccess || per_sm < 1) { \
+      cudaGetLastError();                                                                                              \
+      per_sm = 1;                                                                                                      \
+    }                                                                                                                  \
+    deep_smem_kernel<G><<<num_sms * per_sm, threads, smem, st>>>(A, counter, tab_tiled, t_lo, k);                      \
+  } while (0)
+  if (group == 4) PIGO_DEEP_SMEM(4);
+  else if (group == 16) PIGO_DEEP_SMEM(16);
+  else if (group == 32) PIGO_DEEP_SMEM(32);
+  else PIGO_DEEP_SMEM(8);
+#undef PIGO_DEEP_SMEM
 }
 
 // Flat loop (option deep_flat=1): every iteration each lane group either fetches its next window or walks one step.  No group

@@ -50,7 +50,15 @@ struct Options {
   std::atomic<long long> tile_tmap{1};      // tile fill: 1 = one TMA tensor copy per tile (cuTensorMapEncodeTiled descriptors), 0 = one bulk copy per tile row
   std::atomic<long long> walk_stats{0};     // 1 = count live lanes per walk iteration of the tile role ("walk_useful" / "walk_iters" read them back)
   std::atomic<long long> tile_core_cap{0};  // largest tile core edge in pixels; 0 = unlimited
+  std::atomic<long long> deep_smem{0};      // deep kernel with the tree records in shared memory: 0 = auto, 1 = on, 2 = off; deep_smem_threads = CTA size
+  std::atomic<long long> deep_smem_threads{256};
+  std::atomic<long long> deep_smem_lo{24};   // first resident tree / number of resident trees of that kernel
+  std::atomic<long long> deep_smem_k{128};
   std::atomic<long long> gather_limit{0};   // trees a gather-role window walks before it goes to the deep kernel; 0 = auto (8 for calls of <= 40 M windows, else 24)
+  std::atomic<long long> queue_cap{0};      // developer knob: cap of the straggler / deep queues in items (0 = sized from the window count)
+  std::atomic<long long> tile_ptab{0};      // fused kernel, tile role: 1 = per-scale offset tables, scale-synchronous rounds (scan_ptab_kernel)
+  std::atomic<long long> ptab_kt{16};       // trees per table of that kernel (survivors go to the deep queue)
+  std::atomic<long long> ptab_ks{24};       // raw cascade trees its gather warps keep in shared memory
   std::atomic<long long> tile_head{0};      // fused kernel, tile role: 0 = classic lane refill from tree 0, N = dense head over the first N trees (scan_head_kernel)
   std::atomic<long long> head_back{12};     // dense head: generic phase parks its live windows and returns to the head below this many live lanes
   std::atomic<long long> deep_flat{0};      // deep kernel loop: 0 = groups of a warp fetch together (round 1), 1 = flat (fetch or step per iteration)
@@ -72,7 +80,7 @@ struct Options {
          {"gather_block", &Options::gather_block}, {"deep_group", &Options::deep_group},
         {"sub_batch", &Options::sub_batch}, {"lanes", &Options::lanes}, {"tile_tail_min", &Options::tile_tail_min},
         {"tile_band_ratio", &Options::tile_band_ratio}, {"timing", &Options::timing}, {"host_stream", &Options::host_stream}, {"copy_chunk", &Options::copy_chunk}, {"stream_taper", &Options::stream_taper},
-        {"deep_flat", &Options::deep_flat}, {"tile_head", &Options::tile_head}, {"tile_core_cap", &Options::tile_core_cap}, {"walk_stats", &Options::walk_stats}, {"tile_tmap", &Options::tile_tmap}, {"gather_limit", &Options::gather_limit}, {"head_back", &Options::head_back}, {"rot_mode", &Options::rot_mode}, {"puploc_mode", &Options::puploc_mode}, {"puploc_stage", &Options::puploc_stage}};
+        {"deep_flat", &Options::deep_flat}, {"tile_head", &Options::tile_head}, {"tile_ptab", &Options::tile_ptab}, {"queue_cap", &Options::queue_cap}, {"ptab_kt", &Options::ptab_kt}, {"ptab_ks", &Options::ptab_ks}, {"tile_core_cap", &Options::tile_core_cap}, {"walk_stats", &Options::walk_stats}, {"tile_tmap", &Options::tile_tmap}, {"gather_limit", &Options::gather_limit}, {"deep_smem", &Options::deep_smem}, {"deep_smem_threads", &Options::deep_smem_threads}, {"deep_smem_lo", &Options::deep_smem_lo}, {"deep_smem_k", &Options::deep_smem_k}, {"head_back", &Options::head_back}, {"rot_mode", &Options::rot_mode}, {"puploc_mode", &Options::puploc_mode}, {"puploc_stage", &Options::puploc_stage}};
     for (const Entry& e : table)
       if (k == e.name) return &(this->*e.field);
     return nullptr;
@@ -148,7 +156,8 @@ constexpr int kMaxLanes = 4;
 
 struct Workspace {
   cudaStream_t stream = nullptr;
-  DevBuf frames, raw, counters, out, nout, plan, tiles, scratch_a, scratch_b, scratch_c, rot_tab;
+  DevBuf frames, raw, counters, out, nout, plan, tiles, scratch_a, scratch_b, scratch_c, rot_tab, ptab;
+  std::vector<int> ptab_sig;                   // geometry the cached per-scale offset tables were built for (empty = none)
   int rot_slot = -1;                           // table slot the cached rotated node table was built for (-1 = none)
   DevBuf deep[kMaxLanes], longq[kMaxLanes];   // Q1 / Q2 per pipeline lane
   cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
@@ -199,7 +208,7 @@ struct Workspace {
     if (busy) cudaEventDestroy(busy);
     for (auto e : copy_events) cudaEventDestroy(e);
     if (copy_stream) cudaStreamDestroy(copy_stream);
-    tiles.release(); scratch_a.release(); scratch_b.release(); scratch_c.release(); rot_tab.release();
+    tiles.release(); scratch_a.release(); scratch_b.release(); scratch_c.release(); rot_tab.release(); ptab.release();
     if (pinned) cudaFreeHost(pinned);
     if (seq) cudaFreeHost(seq);
     if (stream) cudaStreamDestroy(stream);
@@ -290,6 +299,7 @@ namespace pigo {
 void launch_scan_gather(const ScanArgs& A, int grid, int max_scale, cudaStream_t st);
 void launch_scan_tiled(const TiledArgs& A, const TileMaps& TM, int grid, int threads, size_t smem, int ni, cudaStream_t st);
 int tiled_max_threads(int ni);
+void launch_ptab_build(const FaceTables& T, const ScaleEntry* plan, const TiledArgs& A, int first_untiled, uint8_t* out, int grid, cudaStream_t st);
 void launch_gray(const uint8_t* rgba, size_t npix, uint8_t* gray, int grid, cudaStream_t st);
 void launch_ycbcr(const uint8_t* y, const uint8_t* cb, const uint8_t* cr, int y_stride, int c_stride, int subsample, int min_x, int min_y,
                   int width, int height, uint8_t* nrgba, uint8_t* gray, int grid, cudaStream_t st);
@@ -297,6 +307,8 @@ void launch_scan_gather2(const TiledArgs& A, int grid, size_t smem, cudaStream_t
 int gather2_ctas_per_sm(size_t smem, int ng, bool rot);
 void launch_rot_table(const FaceTables& T, const ScaleEntry* plan, int nscales, int slot, RotNode* out, int grid, cudaStream_t st);
 void launch_deep(const ScanArgs& A, unsigned long long* counter, int grid, int group, cudaStream_t st);
+void launch_deep_smem(const ScanArgs& A, unsigned long long* counter, const uint8_t* tab_tiled, int num_sms, int threads, int group, int t_lo, int k,
+                      cudaStream_t st);
 int gather_max_ctas_per_sm(int depth, bool rot);
 void launch_finalize(const RawDet* raw, const int32_t* raw_count, int cap, const ScaleEntry* plan, int nscales, pigo_det* out,
                      int32_t* n_out, int nframes, cudaStream_t st);

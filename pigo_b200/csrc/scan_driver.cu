@@ -97,15 +97,20 @@ static TilePlan plan_bands(const std::vector<ScaleEntry>& plan, uint32_t tile_by
 // Shared-memory layout of the fused kernel: mbarriers (384 B) | cascade prefix | per-warp tiles (128-byte aligned).
 struct FusedLayout {
   bool ok = false;
-  size_t tiles_off = 0, head_off = 0, ring_off = 0;
+  size_t tiles_off = 0, head_off = 0, ring_off = 0, ptab_off = 0;
   uint32_t tile_bytes = 0;
 };
-static FusedLayout fused_layout(int W, int ks, size_t smem_cap_req, int head_trees = 0) {
+static FusedLayout fused_layout(int W, int ks, size_t smem_cap_req, int head_trees = 0, int kt = 0) {
   FusedLayout L;
   const size_t casc_bytes = ((size_t)ks * kTreeRec + 15) & ~(size_t)15;   // TMA bulk copies move multiples of 16 bytes
   L.head_off = 384 + casc_bytes;
   L.ring_off = L.head_off + (size_t)(head_trees > 0 ? kHeadMaxScales * head_trees * 256 : 0);
   L.tiles_off = (L.ring_off + (size_t)(head_trees > 0 ? W * kRing * kRingEntry : 0) + 127) & ~(size_t)127;
+  if (kt > 0) {   // scan_ptab_kernel: control words up to 448, raw prefix, two table buffers 16 bytes apart
+    const size_t stride = ((size_t)kt * kTreeRec + 15) & ~(size_t)15;
+    L.ptab_off = 448 + casc_bytes;
+    L.tiles_off = (L.ptab_off + 2 * stride + 16 + 127) & ~(size_t)127;
+  }
   if (W <= 0 || L.tiles_off + 4096 * (size_t)W >= kSmemPerCta) return L;
   // fused_smem_kb < 227 leaves the rest of the SM's 256 KB to L1 (which the gather warps' pixel loads live in)
   size_t smem_cap = kSmemPerCta;
@@ -122,6 +127,7 @@ struct FusedPlan {
   TilePlan tp;
   int W = 0, ks = 0, ni = 1;
   int head = 0;   // trees of the dense head (0 = classic tile role)
+  int kt = 0;     // trees of the per-scale offset tables (0 = classic tile role)
 };
 static FusedPlan plan_fused(const std::vector<ScaleEntry>& plan, int ntrees, int batch_frames = 1 << 20) {
   FusedPlan P;
@@ -139,8 +145,14 @@ static FusedPlan plan_fused(const std::vector<ScaleEntry>& plan, int ntrees, int
   // Optional cap on the tile core (developer knob; more, shorter tiles).
   long long core_cap = g_opt.tile_core_cap.load();
   if (core_cap <= 0) core_cap = 512;   // (measured: 16/32-pixel cores for a single frame are SLOWER, 0.26 vs 0.22 ms: tile fills dominate)
+  // per-scale offset tables: NI = 1, no head, its own (shorter) raw prefix for the gather warps
+  if (g_opt.tile_ptab.load() != 0 && P.ni == 1 && P.W > 0) {
+    P.kt = (int)std::min<long long>(std::min<long long>(std::max<long long>(1, g_opt.ptab_kt.load()), ntrees), 60);
+    P.ks = (int)std::min<long long>(std::min<long long>(std::max<long long>(1, g_opt.ptab_ks.load()), ntrees), fit);
+    P.head = 0;
+  }
   auto plan_with = [&](int head) {
-    P.L = fused_layout(P.W, P.ks, (size_t)std::max<long long>(0, g_opt.fused_smem_kb.load()) * 1024, head);
+    P.L = fused_layout(P.W, P.ks, (size_t)std::max<long long>(0, g_opt.fused_smem_kb.load()) * 1024, head, P.kt);
     P.tp = TilePlan();
     if (P.L.ok)
       P.tp = plan_bands(plan, P.L.tile_bytes, max_scale, (int)std::max<long long>(100, g_opt.tile_band_ratio.load()),
@@ -157,6 +169,19 @@ static FusedPlan plan_fused(const std::vector<ScaleEntry>& plan, int ntrees, int
       if (plan[B.scale_lo + B.nscales - 1].s > 255) ok = false;
     }
     if (!ok) { P.head = 0; plan_with(0); }
+  }
+  if (P.kt > 0) {
+    // every tiled ladder entry needs a table slot (32 at most) and unsigned 16-bit offsets
+    bool ok = P.L.ok && P.tp.nbands > 0 && P.tp.first_untiled <= 32;
+    for (int b = 0; ok && b < P.tp.nbands; ++b) {
+      const TileBand& B = P.tp.band[b];
+      if ((long long)B.rows_t * (B.pitch + 1) >= 65536) ok = false;
+    }
+    if (!ok) {   // fall back to the classic kernel with the classic prefix
+      P.kt = 0;
+      P.ks = (int)std::min<long long>(std::min<long long>(std::max<long long>(1, g_opt.tile_ks.load()), ntrees), fit);
+      plan_with(0);
+    }
   }
   return P;
 }
@@ -327,11 +352,15 @@ int run_scan(FaceReplica* c, Workspace* w, int lane, ScanArgs& A, unsigned long 
   // ---- queues
   const uint64_t total_windows = (uint64_t)A.wins_per_frame * A.nframes;
   const uint64_t q1_cap = std::min<uint64_t>(total_windows / 16 + 65536, 1ull << 26);
-  const uint64_t q2_cap = std::min<uint64_t>(total_windows / 32 + 65536, 1ull << 26);
+  const uint64_t q2_cap = std::min<uint64_t>(total_windows / (g_opt.tile_ptab.load() != 0 ? 16 : 32) + 65536, 1ull << 26);
+  // developer knob: tiny queues force the "queue full" paths of every producer (tests)
+  const long long qlim = g_opt.queue_cap.load();
+  const uint64_t q1_use = qlim > 0 ? std::min<uint64_t>(q1_cap, (uint64_t)qlim) : q1_cap;
+  const uint64_t q2_use = qlim > 0 ? std::min<uint64_t>(q2_cap, (uint64_t)qlim) : q2_cap;
   if ((rc = w->deep[lane].reserve(q1_cap * sizeof(DeepItem)))) return rc;
   if ((rc = w->longq[lane].reserve(q2_cap * sizeof(DeepItem)))) return rc;
-  A.deep = (DeepItem*)w->deep[lane].p; A.deep_cap = (uint32_t)q1_cap;
-  A.longq = (DeepItem*)w->longq[lane].p; A.long_cap = (uint32_t)q2_cap;
+  A.deep = (DeepItem*)w->deep[lane].p; A.deep_cap = (uint32_t)q1_use;
+  A.longq = (DeepItem*)w->longq[lane].p; A.long_cap = (uint32_t)q2_use;
 
   TiledArgs T{};
   T.scan = A;
@@ -393,6 +422,28 @@ int run_scan(FaceReplica* c, Workspace* w, int lane, ScanArgs& A, unsigned long 
       F.aligned = ((A.dim % 16 == 0) && (A.frame_stride % 16 == 0) && (((uintptr_t)A.frames) % 16 == 0)) ? 1 : 0;
       long long grid = num_sms;
       if (Wg == 0) grid = std::max<long long>(1, std::min<long long>(num_sms, (long long)((F.total_tiles + W - 1) / W)));
+      if (P.kt > 0) {
+        // per-scale offset tables: rounds of W tiles of one band; tables cached per workspace for this geometry
+        F.kt = P.kt;
+        F.ptab_stride = (uint32_t)(((size_t)P.kt * kTreeRec + 15) & ~(size_t)15);
+        F.ptab_off = (uint32_t)P.L.ptab_off;
+        F.rounds_per_frame = 0;
+        std::vector<int> sig = {P.kt, tp.first_untiled, W};
+        for (int b = 0; b < tp.nbands; ++b) {
+          F.band_rounds[b] = (uint32_t)((tp.band[b].ntiles + W - 1) / W);
+          F.rounds_per_frame += F.band_rounds[b];
+          sig.push_back(tp.band[b].scale_lo); sig.push_back(tp.band[b].nscales); sig.push_back(tp.band[b].pitch); sig.push_back(tp.band[b].halo_lo);
+        }
+        if (w->ptab_sig != sig || w->ptab.p == nullptr) {
+          if ((rc = w->ptab.reserve((size_t)tp.first_untiled * F.ptab_stride + 64))) return rc;
+          launch_ptab_build(A.tab, A.plan, F, tp.first_untiled, (uint8_t*)w->ptab.p, num_sms * 4, st);
+          g_launches++;
+          if ((rc = check_launch("offset tables"))) return rc;
+          w->ptab_sig = sig;
+        }
+        F.ptab = (const uint8_t*)w->ptab.p;
+        if (Wg == 0) grid = std::max<long long>(1, std::min<long long>(num_sms, (long long)F.rounds_per_frame * A.nframes));
+      }
       const size_t smem = P.L.tiles_off + (size_t)P.L.tile_bytes * W;
       TileMaps TM{};
       F.use_tmap = (F.aligned && g_opt.tile_tmap.load() != 0) ? 1 : 0;
@@ -442,8 +493,18 @@ int run_scan(FaceReplica* c, Workspace* w, int lane, ScanArgs& A, unsigned long 
   {
     timing_begin(T_DEEP, st);
     int group = (int)g_opt.deep_group.load();
-    if (group != 8 && group != 16 && group != 32) group = small_call ? 32 : 8;   // small call: the latency of a full survivor matters
-    launch_deep(A, d_work + 3, num_sms * 8, group, st);
+    const long long ds = g_opt.deep_smem.load();
+    const bool smem_deep = !rot && A.tab.depth == 6 && c->tiled_tab.p != nullptr && (ds == 1 || (ds == 0 && false));
+    if (smem_deep) {
+      if (group != 4 && group != 8 && group != 16 && group != 32) group = 8;
+      int threads = (int)g_opt.deep_smem_threads.load();
+      threads = std::min(1024, std::max(128, threads)) & ~31;
+      launch_deep_smem(A, d_work + 3, (const uint8_t*)c->tiled_tab.p, num_sms, threads, group, (int)std::min<long long>(std::max<long long>(0, g_opt.deep_smem_lo.load()), 1 << 20),
+                       (int)std::min<long long>(std::max<long long>(2, g_opt.deep_smem_k.load()), 1 << 20), st);
+    } else {
+      if (group != 8 && group != 16 && group != 32) group = small_call ? 32 : 8;   // small call: the latency of a full survivor matters
+      launch_deep(A, d_work + 3, num_sms * 8, group, st);
+    }
     timing_end(T_DEEP, st);
     g_launches++;
     if ((rc = check_launch("deep scan"))) return rc;

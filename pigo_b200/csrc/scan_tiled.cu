@@ -19,6 +19,8 @@
 //    blocks, pixels by ld.global.nc.
 //
 // Scores are float32 sums in tree order and the result is bit-identical to the reference.
+#include <algorithm>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -28,37 +30,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// ---- TMA bulk copy of the cascade prefix -------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
-               : "memory");
-}
-// One tile = one 3-D tensor copy (x = byte column, y = row, z = frame); out-of-frame parts of the box are zero-filled and
-// count towards the transaction bytes, so the barrier always expects the whole box.
-__device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-               "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
 
 constexpr uint32_t kCascOff = 384;  // mbarriers live in the first 272 bytes of shared memory, then the scale lookup table
 // Window size -> ladder entry, for the queue items of the tile warps (their lanes carry the size, not the index): one byte per
@@ -697,6 +668,408 @@ __global__ void __launch_bounds__(MAXT, 1) scan_tiled_kernel(const TiledArgs A, 
 }
 
 // =============================================================================================================
+// Per-scale offset tables (round 2, option tile_ptab).  Same warp specialisation, tiles, queues and results as the classic
+// kernel; what changes is WHERE the tile role's node data comes from.  The classic walk derives a node's two sample positions
+// from four int8 codes, the window size and the tile pitch at every level (3 PRMT, 4 IMAD, 3 SHF, 2 LEA, 2 IMAD: 24 instructions
+// per level, ncu r02g: issue 74 %).  Here every tiled ladder entry has its own table of the first kt trees in global memory
+// (ptab_kernel): a node is ONE word holding the two tile offsets ((code*s)>>8)*pitch + ((code*s)>>8), biased by
+// halo*(pitch+1) so that both are unsigned 16-bit, and a level is LDS, LOP, 2 x IADD-class, 2 x LDS.U8, ISETP, index update.
+// A table depends on the scale, so the tile warps of a CTA walk the scales in step: the CTA works in ROUNDS (tile_warps
+// consecutive tiles of one band, assigned statically: round g -> CTA g % gridDim), every warp visits the band's scales in
+// order, and two table buffers in shared memory hold the current and the next scale of the sequence.  A warp may have lanes in
+// both (lane refill continues across a scale change); it LEAVES a scale when its last lane of that scale is done or evicted
+// (mbarrier arrive), the warp that completes the barrier issues the TMA bulk copy of the table two steps ahead into the freed
+// buffer, and a warp ENTERS the next scale when that copy has landed (mbarrier phase).  Windows alive after kt trees go to the
+// deep queue.  MEASURED (profiles/sweeps_r02.txt): SLOWER than the classic kernel -- see DESIGN.md; kept as a tested option.
+constexpr uint32_t kPtCtl = 384;    // full[0..1], empty[0..1] mbarriers (8 bytes each), then the two "filled for sequence" words
+constexpr uint32_t kPtCasc = 448;   // raw cascade prefix of the gather role
+constexpr uint32_t kPtGap = 16;     // bytes between the two table buffers ("one past the last tree" of buffer 0 is not buffer 1)
+
+__device__ __forceinline__ int pt_band_of(const TiledArgs& A, uint32_t rem, uint32_t* rib) {
+  int b = 0;
+  while (b + 1 < A.nbands && rem >= A.band_rounds[b]) { rem -= A.band_rounds[b]; ++b; }
+  *rib = rem;
+  return b;
+}
+// Table of the sequence element `steps` after (round g, band scale k) in this CTA's order; nullptr past the CTA's last round.
+__device__ __forceinline__ const uint8_t* pt_table_after(const TiledArgs& A, unsigned long long g, int k, int steps, unsigned long long total_rounds) {
+  uint32_t rib;
+  int b = pt_band_of(A, (uint32_t)(g % A.rounds_per_frame), &rib);
+  for (int i = 0; i < steps; ++i) {
+    if (++k >= A.band[b].nscales) {
+      k = 0;
+      g += gridDim.x;
+      if (g >= total_rounds) return nullptr;
+      b = pt_band_of(A, (uint32_t)(g % A.rounds_per_frame), &rib);
+    }
+  }
+  return A.ptab + (size_t)(A.band[b].scale_lo + k) * A.ptab_stride;
+}
+
+// Finishes one window on the global tables from tree tv on (a queue was full: pathological, slow, correct).
+// pix = tile address of the window centre.
+// (arguments by value: a reference to the kernel's parameter struct would force a local copy of all of it)
+__device__ __noinline__ void pt_finish_slow(const int8_t* codes, const float* preds, const float* thresh, int ntrees, int* raw_count, RawDet* raw, int cap,
+                                            const uint8_t* smem, uint32_t pix, int pitch, int s, int tv, float acc, int frame, uint32_t wid) {
+  float thr = 0.f;
+  for (; tv < ntrees; ++tv) {
+    const int* tc = reinterpret_cast<const int*>(codes + (size_t)tv * 256);
+    int idx = 1;
+    for (int j = 0; j < 6; ++j) {
+      const int cw = __ldg(tc + idx);
+      const int o1 = ((sx0(cw) * s) >> 8) * pitch + ((sx1(cw) * s) >> 8);
+      const int o2 = ((sx2(cw) * s) >> 8) * pitch + ((sx3(cw) * s) >> 8);
+      idx = 2 * idx + (smem[pix + o1] <= smem[pix + o2] ? 1 : 0);      // core/pigo.go:129-135
+    }
+    acc += __ldg(preds + (size_t)tv * 64 + idx - 64);                    // :137
+    thr = __ldg(thresh + tv);
+    if (acc <= thr) return;                                              // :139-141
+  }
+  const float q = acc - thr;                                             // :144
+  if (q > 0.0f) {                                                        // :246
+    const int pos = atomicAdd(raw_count + frame, 1);
+    if (pos < cap) raw[(size_t)frame * cap + pos] = RawDet{wid, q};
+  }
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) scan_ptab_kernel(const TiledArgs A, const __grid_constant__ TileMaps TM) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t wbar = smem_base + 16 + 8 * warp;   // per-warp mbarrier: tile arrival
+  const uint32_t fullbar = smem_base + kPtCtl;       // + 8 * buffer: table arrival
+  const uint32_t emptybar = smem_base + kPtCtl + 16; // + 8 * buffer: every tile warp has left the table (count = tile warps)
+  unsigned int* issued = reinterpret_cast<unsigned int*>(smem + kPtCtl + 32);   // sequence number each buffer was last filled for
+  const uint32_t casc = kPtCasc;
+  const uint32_t casc_bytes = (uint32_t)A.ks * kTreeRec;
+  const uint32_t tab0 = A.ptab_off, tab_bytes = (uint32_t)A.kt * kTreeRec, bstride = A.ptab_stride + kPtGap;
+  const uint32_t my_tile = A.tiles_off + (uint32_t)warp * A.tile_bytes;
+  const int W = A.tile_warps;
+  const ScanArgs& S = A.scan;
+  const unsigned long long total_rounds = (unsigned long long)A.rounds_per_frame * (unsigned long long)S.nframes;
+
+  if (lane == 0 && warp < W) mbar_init(wbar, 1);
+  if (threadIdx.x == 0) {
+    mbar_init(fullbar, 1); mbar_init(fullbar + 8, 1);
+    mbar_init(emptybar, (uint32_t)W); mbar_init(emptybar + 8, (uint32_t)W);
+    issued[0] = 0; issued[1] = 1;
+  }
+  if (threadIdx.x < kLutSizes) smem[kLutOff + threadIdx.x] = 0xff;
+  stage_cascade(A, smem_base, casc, (casc_bytes + 15u) & ~15u);   // (its fence + barrier also publish the barriers above)
+  if ((int)threadIdx.x < S.nscales && threadIdx.x < 255) {
+    const int sz = S.plan[threadIdx.x].s;
+    if (sz >= 0 && sz < kLutSizes) smem[kLutOff + sz] = (uint8_t)threadIdx.x;
+  }
+  if (threadIdx.x == 0 && blockIdx.x < total_rounds) {            // the first two tables of this CTA's sequence
+    for (int i = 0; i < 2; ++i) {
+      const uint8_t* src = pt_table_after(A, blockIdx.x, 0, i, total_rounds);
+      if (src) {
+        mbar_expect_tx(fullbar + 8 * i, A.ptab_stride);
+        tma_bulk_g2s(smem_base + tab0 + (uint32_t)i * bstride, src, A.ptab_stride, fullbar + 8 * i);
+      }
+    }
+  }
+  __syncthreads();
+
+  if (warp >= W) {
+    const uint32_t g_end = casc + (uint32_t)min(A.ks, max(1, A.gather_limit)) * kTreeRec;
+    if (A.gather_ni >= 2) gather_role<2, 0>(A, smem, casc, g_end);
+    else gather_role<1, 0>(A, smem, casc, g_end);
+    return;
+  }
+
+  uint32_t tile_phase = 0;
+  const bool all_resident = A.kt >= S.tab.ntrees;   // then surviving a table means surviving the cascade
+  uint32_t q_round = 0;                             // sequence number of band scale 0 of the current round
+
+  for (unsigned long long g = blockIdx.x; g < total_rounds; g += gridDim.x) {
+    const int frame = (int)(g / A.rounds_per_frame);
+    uint32_t rib;
+    const int b = pt_band_of(A, (uint32_t)(g % A.rounds_per_frame), &rib);
+    const TileBand B = A.band[b];
+    const int tf = (int)rib * W + warp;
+    const bool has_tile = tf < B.ntiles;
+    const int ty = tf / B.tiles_x, tx = tf - ty * B.tiles_x;
+    const int cx0 = B.org_x + tx * B.core, cy0 = ty * B.core;
+    const int gx0 = cx0 - B.halo_lo, gy0 = cy0 - B.halo_lo;
+    const int pitch = B.pitch;
+    const uint32_t bias = (uint32_t)(B.halo_lo * (pitch + 1));
+
+    // leaving band scale kk of this round (sequence q = q_round + kk): arrive on the buffer's "empty" barrier; whoever sees the
+    // phase complete (at least the warp that arrived last) and wins the claim on the sequence number refills the buffer with
+    // the table two steps ahead.  The refill is ordered after every warp's reads by the barrier (arrive = release, test = acquire).
+    auto leave = [&](int kk) {
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t q = q_round + (uint32_t)kk, buf = q & 1u;
+        mbar_arrive(emptybar + 8 * buf);
+        if (mbar_test(emptybar + 8 * buf, (q >> 1) & 1u) && atomicCAS(&issued[buf], q, q + 2u) == q) {
+          const uint8_t* src = pt_table_after(A, g, kk, 2, total_rounds);
+          if (src) {
+            mbar_expect_tx(fullbar + 8 * buf, A.ptab_stride);
+            tma_bulk_g2s(smem_base + tab0 + buf * bstride, src, A.ptab_stride, fullbar + 8 * buf);
+          }
+        }
+      }
+    };
+
+    // ---- per-scale window sub-grids of this tile: lane l describes band scale l
+    int sc_i0 = 0, sc_j0 = 0, sc_nj = 0, sc_n = 0;
+    ScaleEntry e{};
+    if (lane < B.nscales) {
+      e = S.plan[B.scale_lo + lane];
+      if (has_tile) {
+        const int i0 = ceil_div_pos(cy0 - e.off, e.step), i1 = min(e.nrows, ceil_div_pos(cy0 + B.core - e.off, e.step));
+        const int j0 = ceil_div_pos(cx0 - e.off, e.step), j1 = min(e.ncols, ceil_div_pos(cx0 + B.core - e.off, e.step));
+        sc_i0 = i0; sc_j0 = j0;
+        sc_nj = max(0, j1 - j0);
+        sc_n = max(0, i1 - i0) * sc_nj;
+      }
+    }
+    int k = -1;   // band scale open for refill (entered); -1 = none yet
+    if (__any_sync(FULL, sc_n > 0)) {
+      // ---- fill the tile (as the classic kernel)
+      wait_frames(S.ready, S.frame_base + (unsigned)frame + 1u);
+      const uint8_t* fb = S.frames + (size_t)frame * S.frame_stride;
+      __syncwarp();
+      if (A.use_tmap) {
+        if (lane == 0) {
+          mbar_expect_tx(wbar, (uint32_t)(B.rows_t * pitch));
+          tma_tile_g2s(smem_base + my_tile, &TM.m[b], gx0, gy0, frame, wbar);
+        }
+        mbar_wait(wbar, tile_phase);
+        tile_phase ^= 1u;
+      } else if (A.aligned) {
+        const int y_lo = max(gy0, 0), y_hi = min(gy0 + B.rows_t, S.rows);
+        const int x_lo = max(gx0, 0), x_hi = min(gx0 + pitch, S.dim);
+        const uint32_t row_bytes = (uint32_t)(x_hi - x_lo);
+        if (lane == 0) mbar_expect_tx(wbar, row_bytes * (uint32_t)(y_hi - y_lo));
+        __syncwarp();
+        for (int y = y_lo + lane; y < y_hi; y += 32)
+          tma_bulk_g2s(smem_base + my_tile + (uint32_t)((y - gy0) * pitch + (x_lo - gx0)), fb + (size_t)y * S.dim + x_lo, row_bytes, wbar);
+        mbar_wait(wbar, tile_phase);
+        tile_phase ^= 1u;
+      } else {
+        const int nbytes = B.rows_t * pitch;
+        for (int q = lane; q < nbytes; q += 32) {
+          const int row = q / pitch, xx = q - row * pitch;
+          const int y = gy0 + row, x = gx0 + xx;
+          if (y >= 0 && y < S.rows && x >= 0 && x < S.dim) smem[my_tile + q] = __ldg(fb + (size_t)y * S.dim + x);
+        }
+      }
+      __syncwarp();
+
+      bool old_open = false;   // band scale k-1 still has live lanes of this warp (its table buffer is still in use)
+      uint32_t cur_tab = tab0 + (q_round & 1u) * bstride;
+      int cur_k = 0, cur_n = 0;
+      int u_step = 0, u_nj = 1, u_ncols = 0, u_br = 0, u_bc = 0, u_s = 0, u_s_old = 0;
+      uint32_t u_wid0 = 0, u_magic = 0;
+      bool exhausted = false;
+      bool alive = false;
+      uint32_t pb = my_tile, tbo = cur_tab, wid = 0;
+      int tleft = 0;
+      float acc = 0.f;
+
+      for (;;) {
+        // ---- leave the older scale once its last lane is gone
+        if (old_open) {
+          const uint32_t old_lo = tab0 + ((q_round + (uint32_t)k - 1u) & 1u) * bstride;
+          if (!__any_sync(FULL, alive && (tbo - old_lo) < bstride)) { leave(k - 1); old_open = false; }
+        }
+        // ---- refill dead lanes from the tile's window list (scale-major)
+        const unsigned need = __ballot_sync(FULL, !alive);
+        if (need) {
+          const int total = __popc(need);
+          if (!exhausted && cur_k + total <= cur_n) {
+            if (!alive) {
+              const uint32_t kk = (uint32_t)(cur_k + __popc(need & lanemask_lt()));
+              const uint32_t i = u_nj > 1 ? __umulhi(kk, u_magic) : kk;
+              const uint32_t j = kk - i * (uint32_t)u_nj;
+              pb = my_tile + (uint32_t)((u_br + (int)i * u_step) * pitch + u_bc + (int)j * u_step) - bias;
+              wid = u_wid0 + i * (uint32_t)u_ncols + j;
+              tbo = cur_tab; acc = 0.f; tleft = A.kt;
+              alive = true;
+            }
+            cur_k += total;
+          } else {
+            unsigned nd = need;
+            while (nd && !exhausted) {
+              if (cur_k == cur_n) {
+                // ---- enter the next band scale: needs the older one left and the table landed.  Lanes still in the older
+                //      scale would hold its buffer (and with it every warp of the CTA) for up to kt trees: they are evicted
+                //      to the straggler queue Q1 instead (a few per cent of the windows; gather-v2 finishes them).
+                if (old_open) {
+                  const uint32_t old_lo = tab0 + ((q_round + (uint32_t)k - 1u) & 1u) * bstride;
+                  const bool mine = alive && (tbo - old_lo) < bstride;
+                  const unsigned mm = __ballot_sync(FULL, mine);
+                  if (mm) {
+                    unsigned qbase = 0;
+                    if (lane == 0) qbase = atomicAdd(S.deep_count, (unsigned)__popc(mm));
+                    qbase = __shfl_sync(FULL, qbase, 0);
+                    const unsigned pos = qbase + __popc(mm & lanemask_lt());
+                    if (mine) {
+                      const int tv = A.kt - tleft;
+                      if (pos < S.deep_cap) S.deep[pos] = DeepItem{wid, pack_frame_si(frame, B.scale_lo + k - 1), tv, acc};
+                      else pt_finish_slow(S.tab.codes, S.tab.preds, S.tab.thresh, S.tab.ntrees, S.raw_count, S.raw, S.cap, smem, pb + bias, pitch, u_s_old, tv, acc, frame, wid);
+                      alive = false;
+                    }
+                  }
+                  leave(k - 1);
+                  old_open = false;
+                  nd = __ballot_sync(FULL, !alive);
+                }
+                if (k + 1 >= B.nscales) { exhausted = true; break; }
+                const uint32_t qn = q_round + (uint32_t)(k + 1);
+                const uint32_t fbq = fullbar + 8 * (qn & 1u), par = (qn >> 1) & 1u;
+                if (!mbar_test(fbq, par)) {
+                  if (nd != FULL) break;          // live lanes: keep walking, look again after the next tree
+                  mbar_wait(fbq, par);
+                }
+                if (k >= 0) {
+                  if (nd != FULL) old_open = true; else leave(k);
+                }
+                ++k;
+                cur_tab = tab0 + (qn & 1u) * bstride;
+                cur_k = 0; cur_n = __shfl_sync(FULL, sc_n, k);
+                u_s_old = u_s;
+                u_s = __shfl_sync(FULL, e.s, k); u_step = __shfl_sync(FULL, e.step, k);
+                const int off = __shfl_sync(FULL, e.off, k), i0 = __shfl_sync(FULL, sc_i0, k), j0 = __shfl_sync(FULL, sc_j0, k);
+                u_nj = __shfl_sync(FULL, sc_nj, k); u_ncols = __shfl_sync(FULL, e.ncols, k);
+                u_br = off + i0 * u_step - gy0;
+                u_bc = off + j0 * u_step - gx0;
+                u_wid0 = __shfl_sync(FULL, e.wbase, k) + (uint32_t)i0 * (uint32_t)u_ncols + (uint32_t)j0;
+                u_magic = u_nj > 1 ? (uint32_t)((0x100000000ull + (unsigned)u_nj - 1) / (unsigned)u_nj) : 0u;
+                continue;
+              }
+              const int avail = cur_n - cur_k;
+              const int rank = __popc(nd & lanemask_lt());
+              if (!alive && rank < avail) {
+                const uint32_t kk = (uint32_t)(cur_k + rank);
+                const uint32_t i = u_nj > 1 ? __umulhi(kk, u_magic) : kk;
+                const uint32_t j = kk - i * (uint32_t)u_nj;
+                pb = my_tile + (uint32_t)((u_br + (int)i * u_step) * pitch + u_bc + (int)j * u_step) - bias;
+                wid = u_wid0 + i * (uint32_t)u_ncols + j;
+                tbo = cur_tab; acc = 0.f; tleft = A.kt;
+                alive = true;
+              }
+              cur_k += min(__popc(nd), avail);
+              nd = __ballot_sync(FULL, !alive);
+            }
+            // ---- tail policy: once the tile is drained, a thin slot group is handed to the straggler queue Q1
+            unsigned live = __ballot_sync(FULL, alive);
+            if (exhausted && live != 0u && __popc(live) < A.tail_min) {
+              unsigned qbase = 0;
+              if (lane == 0) qbase = atomicAdd(S.deep_count, (unsigned)__popc(live));
+              qbase = __shfl_sync(FULL, qbase, 0);
+              const unsigned pos = qbase + __popc(live & lanemask_lt());
+              if (alive) {
+                const uint32_t old_lo = tab0 + ((q_round + (uint32_t)k - 1u) & 1u) * bstride;
+                const bool in_old = old_open && (tbo - old_lo) < bstride;
+                const int tv = A.kt - tleft;
+                if (pos < S.deep_cap) S.deep[pos] = DeepItem{wid, pack_frame_si(frame, B.scale_lo + (in_old ? k - 1 : k)), tv, acc};
+                else pt_finish_slow(S.tab.codes, S.tab.preds, S.tab.thresh, S.tab.ntrees, S.raw_count, S.raw, S.cap, smem, pb + bias, pitch, in_old ? u_s_old : u_s, tv, acc, frame, wid);
+                alive = false;
+              }
+              live = 0u;
+            }
+            if (live == 0u) {
+              if (exhausted) break;      // round done for this warp
+              continue;                  // nothing to walk: leave the older scale / wait for the table at the top
+            }
+          }
+        }
+        if (!alive) { tbo = cur_tab; pb = my_tile; }   // dead lanes walk a harmless dummy (tree 0 of a landed table at the tile origin)
+
+        if (A.stats != nullptr) {
+          const unsigned nlive = __popc(__ballot_sync(FULL, alive));
+          if (lane == 0) { atomicAdd(A.stats, (unsigned long long)nlive); atomicAdd(A.stats + 1, 1ull); }
+        }
+        // ================= one tree per live lane ==================================================================
+        int idx = 1;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const uint32_t nw = *reinterpret_cast<const uint32_t*>(smem + tbo + 4 * idx);   // the node's two tile offsets
+          const uint32_t p1 = smem[pb + (nw & 0xffffu)], p2 = smem[pb + (nw >> 16)];
+          idx = 2 * idx + (p1 <= p2 ? 1 : 0);                                             // core/pigo.go:129-135
+        }
+        const float pred = *reinterpret_cast<const float*>(smem + tbo + 4 * idx);         // leaf (words 64..127)
+        const float thr = *reinterpret_cast<const float*>(smem + tbo + 512);
+        acc += pred;                                          // core/pigo.go:137 (float32, tree order)
+        alive = alive && !(acc <= thr);                       // :139-141
+        tbo += kTreeRec;
+        --tleft;
+        const bool at_end = alive && tleft == 0;
+        const unsigned mb = __ballot_sync(FULL, at_end);
+        if (mb) {                                             // some windows passed the last table tree (rare)
+          if (all_resident) {
+            if (at_end) {
+              const float q = acc - thr;                      // :144
+              if (q > 0.0f) {                                 // :246
+                const int pos = atomicAdd(S.raw_count + frame, 1);
+                if (pos < S.cap) S.raw[(size_t)frame * S.cap + pos] = RawDet{wid, q};
+              }
+              alive = false;
+            }
+          } else {
+            unsigned qbase = 0;
+            if (lane == 0) qbase = atomicAdd(S.long_count, (unsigned)__popc(mb));
+            qbase = __shfl_sync(FULL, qbase, 0);
+            const unsigned pos = qbase + __popc(mb & lanemask_lt());
+            if (at_end) {
+              const uint32_t old_lo = tab0 + ((q_round + (uint32_t)k - 1u) & 1u) * bstride;
+              const bool in_old = old_open && (tbo - old_lo) < bstride;
+              if (pos < S.long_cap) S.longq[pos] = DeepItem{wid, pack_frame_si(frame, B.scale_lo + (in_old ? k - 1 : k)), A.kt, acc};
+              else pt_finish_slow(S.tab.codes, S.tab.preds, S.tab.thresh, S.tab.ntrees, S.raw_count, S.raw, S.cap, smem, pb + bias, pitch, in_old ? u_s_old : u_s, A.kt, acc, frame, wid);
+              alive = false;
+            }
+          }
+        }
+      }
+      if (old_open) leave(k - 1);   // (cannot happen: no live lanes -> left at the top of the loop; kept for safety)
+      if (k >= 0) leave(k);
+    }
+    // ---- scales this warp never entered (no tile in this round, or no windows): pass through, in order
+    for (int kk = k + 1; kk < B.nscales; ++kk) {
+      const uint32_t qn = q_round + (uint32_t)kk;
+      mbar_wait(fullbar + 8 * (qn & 1u), (qn >> 1) & 1u);
+      leave(kk);
+    }
+    q_round += (uint32_t)B.nscales;
+  }
+}
+
+// One thread per (tiled ladder entry, tree < kt, record word): the node words of the per-scale tables.
+struct PtabGeom {
+  int32_t nscales;                 // tiled ladder entries
+  int32_t pitch[32], halo[32];     // of the band each entry belongs to
+};
+__global__ void __launch_bounds__(256) ptab_kernel(FaceTables T, const ScaleEntry* __restrict__ plan, PtabGeom G, int kt, uint32_t stride,
+                                                   uint8_t* __restrict__ out) {
+  const int words = kTreeRec / 4;
+  const size_t total = (size_t)G.nscales * kt * words;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int wd = (int)(i % words);
+    const size_t st = i / words;
+    const int t = (int)(st % (size_t)kt), si = (int)(st / (size_t)kt);
+    uint32_t v = 0;
+    if (wd >= 1 && wd < 64) {
+      const int s = plan[si].s, pitch = G.pitch[si], halo = G.halo[si];
+      const int8_t* cd = T.codes + (size_t)t * 256 + 4 * wd;
+      const int o1 = (((int)cd[0] * s) >> 8) * pitch + (((int)cd[1] * s) >> 8) + halo * (pitch + 1);   // core/pigo.go:126-127
+      const int o2 = (((int)cd[2] * s) >> 8) * pitch + (((int)cd[3] * s) >> 8) + halo * (pitch + 1);
+      v = (uint32_t)(o1 & 0xffff) | ((uint32_t)(o2 & 0xffff) << 16);
+    } else if (wd >= 64 && wd < 128) {
+      v = __float_as_uint(T.preds[(size_t)t * 64 + (wd - 64)]);
+    } else if (wd == 128) {
+      v = __float_as_uint(T.thresh[t]);
+    }
+    *reinterpret_cast<uint32_t*>(out + (size_t)si * stride + (size_t)t * kTreeRec + 4 * (size_t)wd) = v;
+  }
+}
+
+// =============================================================================================================
 // Dense-head variant of the fused kernel (round 2).  Same warp specialisation, same tiles, same queues; the tile role is
 // split in two phases so that the first trees -- tree 0 and 1 are 63 % of all tree walks, and every window walks tree 0 --
 // run on a cheaper instruction stream:
@@ -1032,7 +1405,23 @@ int gather2_ctas_per_sm(size_t smem, int ng, bool rot) {
 
 int tiled_max_threads(int ni) { return ni == 1 ? 1024 : (ni == 2 ? 768 : 512); }
 
+void launch_ptab_build(const FaceTables& T, const ScaleEntry* plan, const TiledArgs& A, int first_untiled, uint8_t* out, int grid, cudaStream_t st) {
+  PtabGeom G{};
+  G.nscales = std::min(first_untiled, 32);
+  for (int b = 0; b < A.nbands; ++b)
+    for (int i = 0; i < A.band[b].nscales; ++i) {
+      const int si = A.band[b].scale_lo + i;
+      if (si < 32) { G.pitch[si] = A.band[b].pitch; G.halo[si] = A.band[b].halo_lo; }
+    }
+  ptab_kernel<<<grid, 256, 0, st>>>(T, plan, G, A.kt, A.ptab_stride, out);
+}
+
 void launch_scan_tiled(const TiledArgs& A, const TileMaps& TM, int grid, int threads, size_t smem, int ni, cudaStream_t st) {
+  if (A.kt > 0) {
+    cudaFuncSetAttribute(scan_ptab_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    scan_ptab_kernel<1024><<<grid, threads, smem, st>>>(A, TM);
+    return;
+  }
   if (A.head_trees > 0) {
     cudaFuncSetAttribute(scan_head_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     scan_head_kernel<1024><<<grid, threads, smem, st>>>(A, TM);

@@ -264,6 +264,17 @@ VARIANTS = [
     {"scan_mode": 3, "deep_flat": 1, "deep_group": 16, "gather_ks": 3},
     {"scan_mode": 0, "tile_head": 2, "tile_warps": 22},                                       # dense head over trees 0..1, ring + generic tail
     {"scan_mode": 0, "tile_head": 1, "tile_warps": 24, "head_back": 1},
+    {"scan_mode": 0, "tile_ptab": 1},                                                         # per-scale offset tables, scale-synchronous rounds
+    {"scan_mode": 0, "tile_ptab": 1, "ptab_kt": 4, "ptab_ks": 6, "tile_warps": 7, "gather_warps": 3},
+    {"scan_mode": 0, "tile_ptab": 1, "ptab_kt": 468, "tile_tail_min": 33, "tile_warps": 12},  # capped at 60 trees; every drained tile spills
+    {"scan_mode": 0, "tile_ptab": 1, "ptab_kt": 5, "tile_tail_min": 0, "gather_warps": 0, "tile_warps": 16},
+    {"scan_mode": 0, "tile_ptab": 1, "ptab_kt": 1, "tile_max_scale": 30, "tile_band_ratio": 110},   # many narrow bands
+    {"scan_mode": 0, "queue_cap": 40, "tile_ks": 4, "gather_ks": 6, "tile_tail_min": 33},     # both queues overflow: producers finish their windows in place
+    {"scan_mode": 0, "queue_cap": 7, "tile_ptab": 1, "ptab_kt": 3, "ptab_ks": 5, "tile_tail_min": 33},
+    {"scan_mode": 3, "queue_cap": 16, "gather_ks": 2},
+    {"scan_mode": 0, "deep_smem": 1, "deep_smem_k": 468, "deep_smem_lo": 0},                                                         # deep kernel, tree records in shared memory
+    {"scan_mode": 0, "deep_smem": 1, "deep_group": 4, "gather_limit": 4, "tile_ks": 6, "deep_smem_threads": 512, "deep_smem_k": 30, "deep_smem_lo": 11},   # + entries below its first resident tree
+    {"scan_mode": 3, "deep_smem": 1, "deep_group": 32, "gather_ks": 3, "deep_smem_threads": 256},
     {"scan_mode": 0, "tile_head": 3, "tile_warps": 6, "tile_ks": 5, "head_back": 16, "tile_tail_min": 33},   # everything spills, tiny prefix
     {"scan_mode": 0, "tile_head": 4, "tile_warps": 12, "tile_ks": 63, "gather_warps": 0, "tile_tail_min": 0},
     {"scan_mode": 0, "tile_head": 2, "tile_ks": 2},                                           # prefix not longer than the head: classic kernel

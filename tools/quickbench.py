@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--rows", type=int, default=1080)
     ap.add_argument("--cols", type=int, default=1920)
     ap.add_argument("--shift", type=float, default=0.2)
+    ap.add_argument("--stats", action="store_true", help="also report the tile role's live lanes per walk iteration (walk_stats)")
     ap.add_argument("--host", action="store_true", help="also time the host API (pinned frames in, detections out) per variant")
     args = ap.parse_args()
     pigo_b200.init(0)
@@ -60,6 +61,15 @@ def main():
         run(); torch.cuda.synchronize()
         kt = {n: pigo_b200.get_option(f"t_{n}_ns") / 1e6 for n in ("tiled", "gather", "deep", "finalize")}
         pigo_b200.set_option("timing", 0)
+        if args.stats:
+            pigo_b200.get_option("walk_iters")
+            pigo_b200.set_option("walk_stats", 1)
+            run(); torch.cuda.synchronize()
+            wu0, wi0 = pigo_b200.get_option("walk_useful"), pigo_b200.get_option("walk_iters")
+            run(); torch.cuda.synchronize()
+            wu, wi = pigo_b200.get_option("walk_useful") - wu0, pigo_b200.get_option("walk_iters") - wi0
+            pigo_b200.set_option("walk_stats", 0)
+            print(f"    tile role: {wi / 1e6:.2f} M walk iterations, {wu / 1e6:.1f} M useful tree walks, {wu / max(wi, 1):.2f} live lanes per iteration", flush=True)
         host_ms = None
         if args.host:
             import ctypes as C

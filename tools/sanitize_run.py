@@ -30,6 +30,7 @@ def cp_of(img, rows, cols, dim, prm=PRM):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true", help="scan kernels only, fewer variants (racecheck is slow)")
+    ap.add_argument("--new", action="store_true", help="only the kernels added late in round 2 (offset tables, shared-memory deep, queue overflow)")
     args = ap.parse_args()
     pigo_b200.init(0)
     clf = pigo_b200.NewPigo().Unpack(pigo_b200.load_cascade("facefinder"))
@@ -40,6 +41,10 @@ def main():
                 {"scan_mode": 3, "gather_ks": 4}, {"scan_mode": 1}, {"tile_ni": 2, "tile_warps": 8, "gather_warps": 0, "tile_prefetch": 1},
                 {"tile_head": 2, "tile_warps": 22}, {"tile_head": 1, "tile_warps": 6, "tile_ks": 5, "tile_tail_min": 33},
                 {"host_stream": 1, "copy_chunk": 1, "sub_batch": 1, "deep_flat": 1}, {"host_stream": 0}, {"walk_stats": 1}]
+    late = [{"tile_ptab": 1}, {"tile_ptab": 1, "ptab_kt": 4, "ptab_ks": 6, "tile_warps": 7, "gather_warps": 3, "tile_tail_min": 33},
+            {"deep_smem": 1, "deep_smem_k": 468, "deep_smem_lo": 0}, {"deep_smem": 1, "deep_group": 4, "gather_limit": 4, "tile_ks": 6, "deep_smem_k": 30, "deep_smem_lo": 11},
+            {"queue_cap": 9, "tile_ks": 4, "gather_ks": 6, "tile_tail_min": 33}, {"queue_cap": 7, "tile_ptab": 1, "ptab_kt": 3, "ptab_ks": 5, "tile_tail_min": 33}]
+    variants = late if args.new else variants + late
     if args.quick:
         variants = variants[:2]
     keys = sorted({k for v in variants for k in v})
