@@ -66,7 +66,7 @@ struct Options {
   std::atomic<long long> puploc_stage{1};   // pair kernel: 0 = all global, 1 = the current stage's node codes staged in shared memory, 2 = + the stage's pixel patch when it fits
   std::atomic<long long> puploc_mode{0};    // RunDetector kernel: 0 = (perturbation, tree)-pair kernel, 1 = warp-per-perturbation kernel
   std::atomic<long long> lanes{1};          // internal streams the groups alternate between
-  std::atomic<long long> tile_tail_min{6};  // tail policy threshold
+  std::atomic<long long> tile_tail_min{10}; // tail policy threshold (sweep r02g: 6 -> 10 is 1 % on the bench workload)
   std::atomic<long long> tile_band_ratio{200};  // a band spans scales up to ratio/100 x its first scale
   std::atomic<long long> timing{0};         // 1 = bracket every kernel with CUDA events (bench.py roofline pass)
   std::atomic<long long>* find(const std::string& k) {
