@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(MAXT, 1) scan_ptab_kernel(const TiledArgs A, c
   if (lane == 0 && warp < W) mbar_init(wbar, 1);
   if (threadIdx.x == 0) {
     mbar_init(fullbar, 1); mbar_init(fullbar + 8, 1);
-    mbar_init(emptybar, (uint32_t)W); mbar_init(emptybar + 8, (uint32_t)W);
+    mbar_init(emptybar, 32u * (uint32_t)W); mbar_init(emptybar + 8, 32u * (uint32_t)W);
     issued[0] = 0; issued[1] = 1;
   }
   if (threadIdx.x < kLutSizes) smem[kLutOff + threadIdx.x] = 0xff;
@@ -801,10 +801,10 @@ __global__ void __launch_bounds__(MAXT, 1) scan_ptab_kernel(const TiledArgs A, c
     // phase complete (at least the warp that arrived last) and wins the claim on the sequence number refills the buffer with
     // the table two steps ahead.  The refill is ordered after every warp's reads by the barrier (arrive = release, test = acquire).
     auto leave = [&](int kk) {
+      const uint32_t q = q_round + (uint32_t)kk, buf = q & 1u;
+      mbar_arrive(emptybar + 8 * buf);   // every lane arrives for itself (it was a reader of the table): count = 32 * tile warps
       __syncwarp();
       if (lane == 0) {
-        const uint32_t q = q_round + (uint32_t)kk, buf = q & 1u;
-        mbar_arrive(emptybar + 8 * buf);
         if (mbar_test(emptybar + 8 * buf, (q >> 1) & 1u) && atomicCAS(&issued[buf], q, q + 2u) == q) {
           const uint8_t* src = pt_table_after(A, g, kk, 2, total_rounds);
           if (src) {
