@@ -409,6 +409,32 @@ def main():
             assert rc == 0
         single["host_api_ms_per_frame"] = float(np.median(hts))
 
+    # ---- configs[1]/[2] at the reference's documented parameters (README: ShiftFactor 0.1 -> 4.1 M windows per 1080p frame):
+    #      64 device-resident frames of the same workload, rank 0, N=1 only
+    doc_params = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        nd = min(64, nf)
+        Wd = pigo_b200.count_windows(ROWS, COLS, PARAMS[0], PARAMS[1], 0.1, PARAMS[3])
+        capd = 4096
+        d_out_d = torch.zeros((nd, capd, 4), dtype=torch.int32, device=f"cuda:{dev}")
+        d_cnt_d = torch.zeros(nd, dtype=torch.int32, device=f"cuda:{dev}")
+        ts = []
+        for it in range(7):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            clf.run_cascade_batch_device(d_frames.data_ptr(), nd, ROWS * COLS, ROWS, COLS, COLS, PARAMS[0], PARAMS[1], 0.1, PARAMS[3], 0.0,
+                                         d_out_d.data_ptr(), capd, d_cnt_d.data_ptr(), st)
+            b.record(stream)
+            torch.cuda.synchronize()
+            if it >= 2:
+                ts.append(a.elapsed_time(b))
+        md = float(np.median(ts))
+        doc_params = {"workload": f"{nd} x 1920x1080 frames of the bench batch, MinSize 20 MaxSize 1000 ShiftFactor 0.1 ScaleFactor 1.1 (README parameters), "
+                                  "device resident, CUDA events, median of 5 after 2 warm-ups",
+                      "windows_per_frame": int(Wd), "ms_per_step": md, "windows_per_s": Wd * nd / (md * 1e-3),
+                      "detections_per_step": int(torch.minimum(d_cnt_d, torch.tensor(capd, device=d_cnt_d.device)).sum())}
+        del d_out_d, d_cnt_d
+
     # ---- configs[3]: 3840x2160 frames, rotated scan at EVERY table slot a = k/32 (rank 0, N=1 only: a sweep, not a scaling case)
     config4 = None
     if rank == 0 and world == 1 and not args.no_extra:
@@ -536,7 +562,7 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": nf * ROWS * COLS, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "single_frame": single, "config4": config4, "config5": config5,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "single_frame": single, "doc_params": doc_params, "config4": config4, "config5": config5,
             "detections_per_step": ndet})
     if world > 1:
         import torch.distributed as dist
