@@ -731,3 +731,112 @@ def test_cpp_sharded_over_every_visible_device():
     assert "== single device" in r.stdout
     need = int(os.environ.get("PIGO_REQUIRE_DEVICES", "1"))
     assert int(r.stdout.split("devices=")[1].split()[0]) >= need
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Randomised geometry / parameter fuzz and full-size (BASELINE configs[2]) properties
+# ---------------------------------------------------------------------------------------------------------------
+def _fuzz_case(rng, sample_gray, case):
+    """One random call.  Half of the cases are built to produce survivors: the reference's sample face (rotated by the call's
+    angle, so that the rotated scan finds it) inside a frame large enough to hold it, MaxSize 1000."""
+    from scipy import ndimage
+    ang = float(rng.choice([0.0, 0.0, rng.uniform(0.01, 1.2)]))
+    shift = float(rng.choice([0.03, 0.05, 0.1, 0.15, 0.2, 0.33, 1.0]))
+    scale = float(rng.choice([1.03, 1.05, 1.1, 1.15, 1.3, 2.0]))
+    kind = int(rng.choice([0, 1, 1, 1, 2]))
+    if kind == 1:
+        rows, cols = int(rng.integers(400, 520)), int(rng.integers(320, 560))
+        mn, mx = int(rng.choice([20, 24, 50, 100])), 1000
+        face = sample_gray if ang == 0.0 else ndimage.rotate(sample_gray, min(ang, 1.0) * 360.0, reshape=False, order=1, mode="nearest").astype(np.uint8)
+        img = rng.integers(0, 256, (rows, cols), dtype=np.uint8)
+        r0, c0 = int(rng.integers(0, rows - 400 + 1)), int(rng.integers(0, cols - 320 + 1))
+        img[r0:r0 + 400, c0:c0 + 320] = face
+        shift = min(shift, 0.2)
+        scale = min(scale, 1.3)
+    else:
+        rows, cols = int(rng.integers(24, 420)), int(rng.integers(24, 520))
+        mn = int(rng.choice([0, 1, 7, 20, 20, 24, 33]))
+        mx = int(rng.choice([mn, mn + 5, 60, 150, 1000]))
+        if kind == 0:
+            img = rng.integers(0, 256, (rows, cols), dtype=np.uint8)
+        else:
+            img = np.full((rows, cols), int(rng.integers(0, 256)), dtype=np.uint8)   # flat: every comparison is a tie
+    dim = cols + int(rng.choice([0, 0, 1, 3, 16, 37]))
+    buf = np.zeros((rows, dim), dtype=np.uint8)
+    buf[:, :cols] = img
+    return buf, rows, cols, dim, (mn, mx, shift, scale), ang, kind
+
+
+def test_random_geometry_and_parameter_fuzz(gpu_face, oracle_face, sample_gray):
+    """40 random calls: frame size, stride, MinSize/MaxSize, ShiftFactor, ScaleFactor, angle and content drawn at random;
+    every one bit-equal to the oracle (core/pigo.go:212-258 incl. the ladder's float64 truncations)."""
+    rng = np.random.default_rng(20260923)
+    total = 0
+    for case in range(40):
+        buf, rows, cols, dim, prm, ang, kind = _fuzz_case(rng, sample_gray, case)
+        g = gpu_face.run_cascade_array(cp_of(buf, rows, cols, dim, prm), ang)
+        o = oracle_face.run_cascade(buf, rows, cols, dim, *prm, ang)
+        assert len(g) == len(o) and g.tobytes() == o.tobytes(), f"case {case}: {rows}x{cols} dim {dim} {prm} angle {ang} kind {kind}"
+        total += len(o)
+    assert total > 100   # the fuzz must exercise survivors (score bits), not only rejections
+
+
+def test_full_size_batch_properties(gpu_face, oracle_face):
+    """BASELINE configs[2] at full size (256 x 1080p, the bench workload): size-independent properties of the batch entry points.
+    (i) sampled frames equal the oracle; (ii) host frames streamed behind the copy == the same frames resident on the device,
+    byte for byte over all 256 frames; (iii) frames are independent: reversing the batch reverses the result; (iv) the README
+    parameters (4.1 M windows per frame) on one frame equal the oracle."""
+    import torch
+    nf, R, C = 256, 1080, 1920
+    base = synth.make_batch(12, R, C, "USF")
+    frames = np.concatenate([base] * ((nf + 11) // 12))[:nf]
+    cp = cp_of(None, R, C, C, TEST_PARAMS)
+    cap = 256
+    host_dets, host_cnt = gpu_face.RunCascadeBatch(frames, cp, 0.0, cap_per_frame=cap)      # host frames (streamed copy)
+    assert int(host_cnt.max()) <= cap
+    for f in (0, 1, 2, 100, 255):                                                           # (i)
+        o = oracle_face.run_cascade(frames[f], R, C, C, *TEST_PARAMS, 0.0)
+        assert host_cnt[f] == len(o) and host_dets[f, :host_cnt[f]].tobytes() == o.tobytes()
+    d = torch.from_numpy(frames).cuda()
+    d_out = torch.zeros((nf, cap, 4), dtype=torch.int32, device="cuda")
+    d_cnt = torch.zeros(nf, dtype=torch.int32, device="cuda")
+    gpu_face.run_cascade_batch_device(d.data_ptr(), nf, R * C, R, C, C, *TEST_PARAMS, 0.0, d_out.data_ptr(), cap, d_cnt.data_ptr())
+    torch.cuda.synchronize()
+    dev_cnt = d_cnt.cpu().numpy()
+    dev_dets = d_out.cpu().numpy().view(np.uint8).reshape(nf, cap * 16)
+    assert (dev_cnt == host_cnt[:nf]).all()                                                 # (ii)
+    hb = np.ascontiguousarray(host_dets).view(np.uint8).reshape(nf, cap * 16)
+    for f in range(nf):
+        assert hb[f, :16 * host_cnt[f]].tobytes() == dev_dets[f, :16 * dev_cnt[f]].tobytes()
+    d_rev = torch.flip(d, dims=[0]).contiguous()                                            # (iii)
+    d_out.zero_(); d_cnt.zero_()
+    gpu_face.run_cascade_batch_device(d_rev.data_ptr(), nf, R * C, R, C, C, *TEST_PARAMS, 0.0, d_out.data_ptr(), cap, d_cnt.data_ptr())
+    torch.cuda.synchronize()
+    rev_cnt = d_cnt.cpu().numpy()
+    rev_dets = d_out.cpu().numpy().view(np.uint8).reshape(nf, cap * 16)
+    assert (rev_cnt[::-1] == dev_cnt).all()
+    for f in range(nf):
+        assert rev_dets[nf - 1 - f, :16 * dev_cnt[f]].tobytes() == dev_dets[f, :16 * dev_cnt[f]].tobytes()
+    # every frame of the batch is one of 12 distinct images: equal images must give equal results (a checksum of checksums)
+    for f in range(12, nf):
+        assert dev_cnt[f] == dev_cnt[f % 12] and dev_dets[f, :16 * dev_cnt[f]].tobytes() == dev_dets[f % 12, :16 * dev_cnt[f]].tobytes()
+    del d, d_rev, d_out, d_cnt
+    g = gpu_face.run_cascade_array(cp_of(frames[2], R, C, C, DOC_PARAMS), 0.0)               # (iv)
+    assert_same(g, oracle_face.run_cascade(frames[2], R, C, C, *DOC_PARAMS, 0.0))
+
+
+def test_full_turn_equals_unrotated_scan_where_the_clamp_is_idle(gpu_face, oracle_face):
+    """SURVEY config 4: angle 32/32 has qcos = 256, qsin = 0, i.e. the unrotated sample points -- so on a frame that is at least as
+    tall as wide (the rotated path clamps COLUMNS with nrows-1, core/pigo.go:168,171) RunCascade(angle 1.0) == RunCascade(angle 0),
+    detection for detection and bit for bit; on a wide frame the clamp quirk makes them differ, and both agree with the oracle."""
+    tall = synth.frame_faces(None, 2160, 1600, shift=(11, 5), noise_seed=4)
+    a0 = gpu_face.run_cascade_array(cp_of(tall, 2160, 1600, 1600, TEST_PARAMS), 0.0)
+    a1 = gpu_face.run_cascade_array(cp_of(tall, 2160, 1600, 1600, TEST_PARAMS), 1.0)
+    assert len(a0) > 20 and a0.tobytes() == a1.tobytes()
+    a2 = gpu_face.run_cascade_array(cp_of(tall, 2160, 1600, 1600, TEST_PARAMS), 7.5)     # angle > 1 is clamped to 1 (:233-235)
+    assert a2.tobytes() == a1.tobytes()
+    wide = synth.frame_faces(None, 600, 1900, shift=(3, 9), noise_seed=5)
+    w0 = gpu_face.run_cascade_array(cp_of(wide, 600, 1900, 1900, TEST_PARAMS), 0.0)
+    w1 = gpu_face.run_cascade_array(cp_of(wide, 600, 1900, 1900, TEST_PARAMS), 1.0)
+    assert_same(w1, oracle_face.run_cascade(wide, 600, 1900, 1900, *TEST_PARAMS, 1.0))
+    assert w0.tobytes() != w1.tobytes()
