@@ -218,7 +218,7 @@ int describe_plan(const std::vector<ScaleEntry>& plan, uint64_t wins, int ntrees
   snprintf(tmp, sizeof(tmp), "\"nscales\": %d, \"windows\": %llu, \"tile_warps\": %d, \"tiles_off\": %zu, ", (int)plan.size(),
            (unsigned long long)wins, P.W, P.L.tiles_off);
   s += tmp;
-  snprintf(tmp, sizeof(tmp), "\"tile_bytes\": %u, \"first_untiled\": %d, \"bands\": [", tile_bytes, tp.first_untiled);
+  snprintf(tmp, sizeof(tmp), "\"tile_bytes\": %u, \"first_untiled\": %d, \"ptab_kt\": %d, \"bands\": [", tile_bytes, tp.first_untiled, P.kt);
   s += tmp;
   for (int b = 0; b < tp.nbands; ++b) {
     const TileBand& B = tp.band[b];

@@ -56,3 +56,29 @@ def test_plan_follows_the_tuning_options():
     finally:
         for k, v in saved.items():
             pigo_b200.set_option(k, v)
+
+
+def test_offset_table_kernel_plan_keeps_the_tile_invariants():
+    """tile_ptab=1 (scan_ptab_kernel) moves the tiles behind two table buffers: same partition / containment invariants, a smaller
+    tile budget, offsets that fit 16 bits, at most 32 tiled ladder entries."""
+    saved = {k: pigo_b200.get_option(k) for k in ("tile_ptab", "ptab_kt", "ptab_ks", "tile_warps")}
+    try:
+        base = _check(1080, 1920, (20, 1000, 0.2, 1.1))
+        pigo_b200.set_option("tile_ptab", 1)
+        for kt, ks, warps in ((16, 24, 24), (4, 6, 7), (60, 48, 12), (1, 1, 24)):
+            pigo_b200.set_option("ptab_kt", kt)
+            pigo_b200.set_option("ptab_ks", ks)
+            pigo_b200.set_option("tile_warps", warps)
+            for geom, prm in (((1080, 1920), (20, 1000, 0.2, 1.1)), ((2160, 3840), (20, 1000, 0.1, 1.1)), ((97, 131), (12, 90, 0.05, 1.05))):
+                p = _check(geom[0], geom[1], prm)
+                if p["ptab_kt"] == 0:        # more than 32 tiled ladder entries: the planner falls back to the classic kernel
+                    assert p["first_untiled"] > 32
+                    continue
+                assert p["ptab_kt"] == min(kt, 60) and p["first_untiled"] <= 32
+                for b in p["bands"]:
+                    assert b["rows_t"] * (b["pitch"] + 1) < 65536
+                if warps == 24 and geom == (1080, 1920) and kt == 16:
+                    assert p["tiles_off"] > base["tiles_off"] and p["tile_bytes"] <= base["tile_bytes"]
+    finally:
+        for k, v in saved.items():
+            pigo_b200.set_option(k, v)
