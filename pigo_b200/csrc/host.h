@@ -67,7 +67,7 @@ struct Options {
   std::atomic<long long> puploc_mode{0};    // RunDetector kernel: 0 = (perturbation, tree)-pair kernel, 1 = warp-per-perturbation kernel
   std::atomic<long long> lanes{1};          // internal streams the groups alternate between
   std::atomic<long long> tile_tail_min{10}; // tail policy threshold (sweep r02g: 6 -> 10 is 1 % on the bench workload)
-  std::atomic<long long> tile_band_ratio{200};  // a band spans scales up to ratio/100 x its first scale
+  std::atomic<long long> tile_band_ratio{0};    // a band spans scales up to ratio/100 x its first scale; 0 = auto (200, or 140 for calls of <= 2 M windows)
   std::atomic<long long> timing{0};         // 1 = bracket every kernel with CUDA events (bench.py roofline pass)
   std::atomic<long long>* find(const std::string& k) {
     struct Entry { const char* name; std::atomic<long long> Options::*field; };
