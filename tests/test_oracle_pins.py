@@ -196,3 +196,26 @@ def test_ycbcr_restatement_is_within_one_of_the_reference_tests_formula():
                     b = min(255, max(0, (yy * 65536 + 116130 * b_ + 32768) >> 16))
                     assert abs(got[dy, dx, 0] - r) <= 1 and abs(got[dy, dx, 1] - g) <= 1 and abs(got[dy, dx, 2] - b) <= 1
                     assert got[dy, dx, 3] == 255
+
+
+def test_c_and_numpy_restatements_agree_on_random_calls(facefinder_bytes, oracle_face, sample_gray):
+    """The two independently written restatements (C, window-vectorised numpy) on 14 random calls -- geometry, stride, size range,
+    ShiftFactor, ScaleFactor, angle, content -- from the same generator the GPU fuzz uses (tests/test_gpu_parity.py::_fuzz_case):
+    identical detections, bit-equal scores.  Half of the cases contain the sample face rotated by the call's angle."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("gpu_parity_cases", os.path.join(os.path.dirname(__file__), "test_gpu_parity.py"))
+    src = open(spec.origin).read()
+    a, b = src.index("def _fuzz_case"), src.index("def test_random_geometry_and_parameter_fuzz")
+    ns = {"np": np}
+    exec(src[a:b], ns)                       # only the case generator (the module itself is GPU-marked)
+    npf = NP.FaceCascade(facefinder_bytes)
+    rng = np.random.default_rng(77)
+    total = 0
+    for case in range(14):
+        buf, rows, cols, dim, prm, ang, kind = ns["_fuzz_case"](rng, sample_gray, case)
+        x = oracle_face.run_cascade(buf, rows, cols, dim, *prm, ang)
+        y = npf.run_cascade(buf, rows, cols, dim, *prm, ang)
+        assert [(d["row"], d["col"], d["scale"], d["q"]) for d in x] == [(d[0], d[1], d[2], d[3]) for d in y], (case, rows, cols, dim, prm, ang)
+        total += len(x)
+    assert total > 50
